@@ -1,0 +1,79 @@
+"""Golden-vector case list shared by ``oracle/make_golden.py`` (which runs the unmodified
+reference in the build container) and ``tests/`` (which replay the cases on the oracle and
+on the CUDA path).  TEST INFRASTRUCTURE.
+
+Each case = synthetic-config kwargs (networks are re-created from seeds, their sha256
+digest is stored in the fixture) + a deterministic parameter batch that plants the edge
+cases the reference branches on:
+  * Vrot == 0  -> rotational stage skipped            (predictspec.py:229-231)
+  * Vrad == 0  -> no Doppler shift                    (predictspec.py:244-245)
+  * Inst_R absent/NaN -> plain np.interp fallback      (likelihood.py:51-55, predictspec.py:288)
+  * requested resolution above the emulator's -> NaN   (smoothing.py:271)
+  * observed pixels outside emulator coverage -> NaN   (smoothing.py:289)
+  * Av >= 5 -> analytic high-extinction branch         (predictsed.py:86-90)
+"""
+import numpy as np
+
+from thepayne_b200 import synth
+
+CASES = {
+    # name: (builder kwargs, n_points, n_flux_rows_stored)
+    'mini_spec': (dict(kind='mini'), 24, 24),
+    'mini_noinst': (dict(kind='mini', drop=['Inst_R'], fixed={'Vrot': 2.5}), 8, 8),
+    'mini_joint': (dict(kind='mini', npoly=3, bands=synth.PROCYON_BANDS, photH=16), 16, 16),
+    'mini_dist': (dict(kind='mini', bands=synth.PROCYON_BANDS[:3], photH=16, photscale=False,
+                       vmic=True), 8, 8),
+    'mini_edge': (dict(kind='mini', obs_range=(5139.0, 5160.0), n_obs=600), 4, 4),
+    'c2': (dict(kind='c2'), 48, 6),
+    'c3': (dict(kind='c3'), 16, 2),
+}
+
+
+def build(name, model_fn):
+    kw = dict(CASES[name][0])
+    kind = kw.pop('kind')
+    drop = kw.pop('drop', [])
+    fixed = kw.pop('fixed', {})
+    base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3}[kind]
+    if not drop and not fixed:
+        return base(model_fn, **kw)
+
+    # build with a wrapper so that the truth used for the mock observation already has the
+    # dropped / fixed parameters applied
+    def mf(cfg, theta):
+        _apply(cfg, drop, fixed)
+        return model_fn(cfg, cfg.theta_true[None, :])
+    cfg = base(mf, **kw)
+    return cfg
+
+
+def _apply(cfg, drop, fixed):
+    keep = [i for i, p in enumerate(cfg.fitpars_i) if p not in drop and p not in fixed]
+    if len(keep) != len(cfg.fitpars_i):
+        cfg.theta_true = cfg.theta_true[keep]
+        cfg.fitpars_i = [cfg.fitpars_i[i] for i in keep]
+        cfg.fixedpars = dict(fixed)
+
+
+def thetas(name, cfg):
+    n = CASES[name][1]
+    th = cfg.draw(n, seed=4321)
+    th[0] = cfg.theta_true
+    ix = {p: i for i, p in enumerate(cfg.fitpars_i)}
+
+    def put(row, par, val):
+        if par in ix and row < n:
+            th[row, ix[par]] = val
+    put(1, 'Vrot', 0.0)
+    put(2, 'Vrad', 0.0)
+    put(3, 'Vrot', 0.0); put(3, 'Vrad', 0.0)
+    put(4, 'Inst_R', 60000.0)            # finer than the emulator -> NaN
+    put(5, 'Av', 6.0)                    # high-extinction branch
+    put(6, 'Vrot', 35.0)
+    put(7, 'Vrad', -40.0)
+    if name == 'mini_spec':
+        put(8, 'Inst_R', 12000.0)        # broad kernel
+        put(9, 'Inst_R', 48900.0)        # sub-pixel kernel (sigma ~ 0.6 px)
+        put(10, 'Vrot', 0.3)
+        put(11, 'Vrad', 250.0)           # mask endpoints move by ~40 px
+    return th

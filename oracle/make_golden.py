@@ -1,0 +1,42 @@
+"""Mint tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden [case ...]
+
+For every case in ``oracle/goldens.py`` the reference's own
+``likelihood.lnlikefn -> genspec -> getspec -> smoothspec -> chi2`` is executed through the
+stub-import harness (``oracle/refharness.py``) and the inputs/outputs are stored:
+theta, the mock observation, reference model flux (first rows), magnitudes and lnL.
+"""
+import os
+import sys
+
+import numpy as np
+
+from oracle import goldens, refharness
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def main(names):
+    os.makedirs(OUT, exist_ok=True)
+    for name in names:
+        cfg = goldens.build(name, refharness.ref_model_fn)
+        th = goldens.thetas(name, cfg)
+        nflux = goldens.CASES[name][2]
+        lnl = refharness.ref_lnlike(cfg, th)
+        fl, mg = refharness.ref_model_fn(cfg, th[:nflux])
+        # ref_model_fn swaps the observation out; mags need all rows
+        _, mg = refharness.ref_model_fn(cfg, th) if cfg.phot is not None else (None, None)
+        d = dict(theta=th, lnl=lnl, obs_wave=cfg.obs_wave, obs_flux=cfg.obs_flux,
+                 obs_eflux=cfg.obs_eflux, fitpars=np.array(cfg.fitpars_i),
+                 digest=np.array(cfg.spec.digest()), flux=fl)
+        if mg is not None:
+            d['mags'] = mg
+            d['obs_phot'] = np.array([cfg.obs_phot[b] for b in cfg.phot.bands])
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
+        print(name, 'ndim', cfg.ndim, 'points', len(th), 'lnl[:4]', lnl[:4],
+              'nan', int(np.isnan(lnl).sum()))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:] or list(goldens.CASES))

@@ -1,0 +1,165 @@
+"""Run the UNMODIFIED reference likelihood path from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  The reference cannot be imported normally here: h5py, astropy,
+dynesty and matplotlib are absent and ``Payne/__init__.py`` pulls all of them in.  The
+recipe: register empty stand-ins for the missing third-party modules,
+register *shell* packages whose ``__path__`` points into the reference tree (so no
+``__init__.py`` runs), import the hot-path modules as they are, and inject random-init
+networks into instances made with ``__new__`` (their constructors only read HDF5).
+
+Nothing here is used on the GPU box: ``/root/reference`` does not exist there.  The only
+consumer is ``oracle/make_golden.py``, which writes ``tests/golden/*.npz``.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get('PAYNE_REFERENCE', '/root/reference')
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, 'Payne'))
+
+
+def _ascii_read(text, **kw):
+    """10-line stand-in for astropy.io.ascii.read: whitespace table -> structured array
+    (only ``highred.py:169`` uses it)."""
+    rows = [ln.split() for ln in text.strip().splitlines() if ln.strip()]
+    names, rows = rows[0], rows[1:]
+    dt = [(names[0], 'U32')] + [(n, 'f8') for n in names[1:]]
+    return np.array([tuple([r[0]] + [float(v) for v in r[1:]]) for r in rows], dtype=dt)
+
+
+_mods = None
+
+
+def load():
+    """Import the reference hot-path modules; returns a namespace of them."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError('reference tree not found at %s' % REF_ROOT)
+    for name in ['h5py', 'dynesty', 'astropy', 'astropy.io']:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    asc = types.ModuleType('astropy.io.ascii')
+    asc.read = _ascii_read
+    sys.modules['astropy.io.ascii'] = asc
+    sys.modules['astropy.io'].ascii = asc
+    sys.modules['astropy'].io = sys.modules['astropy.io']
+    pk = types.ModuleType('Payne')
+    pk.__path__ = [os.path.join(REF_ROOT, 'Payne')]
+    pk.__abspath__ = os.path.join(REF_ROOT, 'Payne') + '/'
+    sys.modules['Payne'] = pk
+    for sub in ['fitting', 'predict', 'train', 'utils']:
+        m = types.ModuleType('Payne.' + sub)
+        m.__path__ = [os.path.join(REF_ROOT, 'Payne', sub)]
+        sys.modules['Payne.' + sub] = m
+        setattr(pk, sub, m)
+    ns = types.SimpleNamespace()
+    for short, full in [('smoothing', 'Payne.utils.smoothing'), ('NNmodels', 'Payne.train.NNmodels'),
+                        ('predictspec', 'Payne.predict.predictspec'), ('photANN', 'Payne.predict.photANN'),
+                        ('highred', 'Payne.predict.highred'), ('predictsed', 'Payne.predict.predictsed'),
+                        ('fitutils', 'Payne.fitting.fitutils'), ('genmod', 'Payne.fitting.genmod'),
+                        ('likelihood', 'Payne.fitting.likelihood')]:
+        setattr(ns, short, importlib.import_module(full))
+    _mods = ns
+    return ns
+
+
+def build_likelihood(cfg):
+    """Reference ``likelihood`` object wired to the synthetic emulators of ``cfg``."""
+    R = load()
+    s = cfg.spec
+    like = R.likelihood.likelihood.__new__(R.likelihood.likelihood)
+    like.verbose = False
+    like.fitargs = {'obs_wave_fit': cfg.obs_wave, 'obs_flux_fit': cfg.obs_flux,
+                    'obs_eflux_fit': cfg.obs_eflux, 'fixedpars': dict(cfg.fixedpars)}
+    (like.spec_bool, like.phot_bool, like.modpoly_bool, like.photscale_bool,
+     like.carbon_bool) = cfg.runbools
+    like.fixedpars = like.fitargs['fixedpars']
+    like.fitpars_i = list(cfg.fitpars_i)
+    like.ndim = len(like.fitpars_i)
+    GM = R.genmod.GenMod()
+    like.GM = GM
+    if like.spec_bool:
+        H1, H2, H3 = s.weights[0].shape[0], s.weights[3].shape[0], s.weights[4].shape[0]
+        model = R.NNmodels.LinNet(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
+        sd = {}
+        for k in range(6):
+            sd['lin%d.weight' % (k + 1)] = torch.from_numpy(s.weights[k].copy())
+            sd['lin%d.bias' % (k + 1)] = torch.from_numpy(s.biases[k].copy())
+        model.load_state_dict(sd)
+        model.eval()
+        model.D_in = s.D_in
+        ann = R.predictspec.ANN.__new__(R.predictspec.ANN)
+        ann.model, ann.wavelength = model, s.wavelength.copy()
+        ann.resolution = np.array(s.resolution, dtype=float)
+        ann.xmin, ann.xmax, ann.inlabels, ann.NNtype = s.xmin, s.xmax, s.inlabels, 'LinNet'
+        PP = R.predictspec.PayneSpecPredict.__new__(R.predictspec.PayneSpecPredict)
+        PP.anns, PP.Canns, PP.NN, PP.NNtype = ann, None, {}, 'LinNet'
+        GM.PP = PP
+    if like.phot_bool:
+        p = cfg.phot
+        like.fitargs['obs_phot'] = cfg.obs_phot
+        H = p.w1.shape[1]
+        nnlist = []
+        for b in range(len(p.bands)):
+            net = R.photANN.Net(6, H, 1)
+            net.load_state_dict({
+                'lin1.weight': torch.from_numpy(p.w1[b].copy()), 'lin1.bias': torch.from_numpy(p.b1[b].copy()),
+                'lin2.weight': torch.from_numpy(p.w2[b].copy()), 'lin2.bias': torch.from_numpy(p.b2[b].copy()),
+                'lin3.weight': torch.from_numpy(p.w3[b].copy()), 'lin3.bias': torch.from_numpy(p.b3[b].copy())})
+            net.xmin, net.xmax = p.xmin, p.xmax
+            nnlist.append(types.SimpleNamespace(model=net))
+        fpp = R.predictsed.FastPayneSEDPredict.__new__(R.predictsed.FastPayneSEDPredict)
+        fpp.filternames = list(p.bands)
+        fpp.anns = R.photANN.fastANN(nnlist, fpp.filternames)
+        fpp.HiAv = R.highred.highAv(fpp.filternames)
+        GM.fppsed, GM.filterarray = fpp, list(p.bands)
+    return like
+
+
+def ref_model(cfg, theta):
+    """Reference model spectrum/mags for each row of theta (via genspec/genphot*)."""
+    like = build_likelihood(cfg)
+    fl, mg = [], []
+    for t in np.asarray(theta, dtype=np.float64):
+        like.lnlikefn_pack = None
+        # replay lnlikefn's packing (likelihood.py:42-72) by calling it with a dummy lnlike
+        captured = {}
+        orig = like.lnlike
+        like.lnlike = lambda specpars=None, photpars=None: captured.update(s=specpars, p=photpars) or 0.0
+        like.lnlikefn(t)
+        like.lnlike = orig
+        if like.spec_bool:
+            _, f = like.GM.genspec(captured['s'], outwave=cfg.obs_wave, modpoly=like.modpoly_bool)
+            fl.append(np.array(f, dtype=np.float64))
+        if like.phot_bool:
+            d = (like.GM.genphot_scaled if like.photscale_bool else like.GM.genphot)(captured['p'])
+            mg.append(np.array([d[b] for b in cfg.phot.bands], dtype=np.float64))
+    return (np.array(fl) if fl else None), (np.array(mg) if mg else None)
+
+
+def ref_model_fn(cfg, theta):
+    """``model_fn`` for synth.build_config driven by the reference itself."""
+    tmp = (cfg.obs_flux, cfg.obs_eflux, cfg.obs_phot)
+    n = len(cfg.obs_wave)
+    cfg.obs_flux, cfg.obs_eflux = np.ones(n), np.ones(n)
+    if cfg.phot is not None:
+        cfg.obs_phot = {b: [0.0, 1.0] for b in cfg.phot.bands}
+    out = ref_model(cfg, theta)
+    cfg.obs_flux, cfg.obs_eflux, cfg.obs_phot = tmp
+    return out
+
+
+def ref_lnlike(cfg, theta):
+    like = build_likelihood(cfg)
+    return np.array([like.lnlikefn(t) for t in np.asarray(theta, dtype=np.float64)])
