@@ -1,0 +1,157 @@
+/*
+ * payne_b200.h -- C ABI of the B200-native batched likelihood path of The Payne.
+ *
+ * The reference (pacargile/ThePayne) is pure Python and has no FFI layer; the boundary it
+ * exposes for this path is a set of Python method signatures.  Each entry point below
+ * names the reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   payne_ctx_create        likelihood.__init__            Payne/fitting/likelihood.py:7-40
+ *                           GenMod._initspecnn/_initphotnn Payne/fitting/genmod.py:15-43
+ *                           ANN.__init__ / readNN          Payne/predict/predictspec.py:31-59,
+ *                                                          Payne/train/NNmodels.py:44-89
+ *                           fastANN.__init__               Payne/predict/photANN.py:97-116
+ *   payne_lnlike_batch      likelihood.lnlikefn + lnlike   Payne/fitting/likelihood.py:42-117
+ *   payne_lnlike_batch_host same, host buffers in/out (what dynesty hands over)
+ *   payne_model_batch       GenMod.genspec / genphot(_scaled)  Payne/fitting/genmod.py:58-187
+ *                           PayneSpecPredict.getspec       Payne/predict/predictspec.py:136-294
+ *                           FastPayneSEDPredict.sed        Payne/predict/predictsed.py:75-103
+ *   payne_ann_eval          ANN.eval / LinNet.forward      Payne/predict/predictspec.py:61-74,
+ *                                                          Payne/train/NNmodels.py:154-168
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative PAYNE_E_* code and never throws; payne_last_error() gives the message of the
+ * last failure on the calling thread.  "dev" pointers are CUDA device pointers on the
+ * context's device, owned by the caller; the context owns only its copies of the network
+ * weights, the observation and its workspaces.  Calls are stream-ordered on `stream`
+ * (a cudaStream_t passed as void*, NULL = legacy default stream) and do not synchronise,
+ * except the *_host entry which returns with the results in host memory.  One context
+ * per device; distinct contexts may be used from distinct threads concurrently.
+ *
+ * NaN semantics follow the reference: NaN is returned (never an error) for observed
+ * pixels outside the emulator's coverage (smoothing.py:289), for a requested resolution
+ * finer than the emulator's (smoothing.py:271) and for NaN inputs.
+ */
+#ifndef PAYNE_B200_H
+#define PAYNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAYNE_ABI_VERSION 1
+
+enum {
+  PAYNE_OK = 0,
+  PAYNE_E_INVALID = -1,   /* bad argument / unsupported shape */
+  PAYNE_E_CUDA = -2,      /* CUDA runtime / driver error */
+  PAYNE_E_NOMEM = -3,
+  PAYNE_E_UNSUPPORTED = -4
+};
+
+/* Named parameters of the sampler vector, in the order of fitstar.fitpars
+ * (Payne/fitting/fitstar.py:50-65).  pc_k continuum coefficients are listed separately. */
+enum {
+  PAYNE_P_TEFF = 0, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VRAD, PAYNE_P_VROT,
+  PAYNE_P_VMIC, PAYNE_P_INSTR, PAYNE_P_LOGR, PAYNE_P_DIST, PAYNE_P_LOGA, PAYNE_P_AV,
+  PAYNE_P_RV, PAYNE_NPAR
+};
+#define PAYNE_MAX_POLY 16
+
+/* MLP arithmetic. PARITY reproduces the reference's fp32 Linear layers (error-compensated
+ * 3xTF32 on the tensor cores, fp32 accumulate); the other two trade accuracy for speed and
+ * do NOT meet the 1e-5 / 1e-3 parity bar (reported separately). SIMT_FP32 is a plain
+ * CUDA-core fp32 FMA implementation kept as an on-device cross-check. */
+enum {
+  PAYNE_PREC_PARITY_3XTF32 = 0,
+  PAYNE_PREC_TF32 = 1,
+  PAYNE_PREC_BF16 = 2,
+  PAYNE_PREC_SIMT_FP32 = 3
+};
+
+/* Spectrum emulator: LinNet (NNmodels.py:140-168); HOST pointers, copied at create.
+ * W[k] is lin{k+1}.weight, row-major [out,in] fp32; b[k] is lin{k+1}.bias. */
+typedef struct {
+  int32_t D_in, H1, H2, H3, D_out;
+  const float* W[6];
+  const float* b[6];
+  const double* xmin;        /* [D_in] */
+  const double* xmax;        /* [D_in] */
+  const double* wavelength;  /* [D_out], strictly increasing */
+  double resolution;         /* sigma-R of the emulator grid (predictspec.py:49) */
+  double encode_offset;      /* 0.5 for LinNet (NNmodels.py:166) */
+} PayneSpecNet;
+
+/* Photometry emulator: stacked per-band Net(6,H,1) (photANN.py:97-106); HOST pointers. */
+typedef struct {
+  int32_t nb, H;
+  const float *w1, *b1;      /* [nb,H,6], [nb,H]  */
+  const float *w2, *b2;      /* [nb,H,H], [nb,H]  */
+  const float *w3, *b3;      /* [nb,H],   [nb]    */
+  const double *xmin, *xmax; /* [6] */
+  const double *hiav;        /* [nb,5] a1,b1,a2,b2,c2 (highred.py:10-25), NaN if absent */
+} PaynePhotNet;
+
+/* Observation (fitargs of likelihood.py:84-112); HOST pointers, copied at create. */
+typedef struct {
+  int32_t n_obs;
+  const double *wave, *flux, *eflux;   /* [n_obs]; wave increasing */
+  int32_t nb;
+  const double *phot_mag, *phot_err;   /* [nb] */
+} PayneObs;
+
+/* How a row of theta maps onto named parameters (likelihood.py:42-72). */
+typedef struct {
+  int32_t ndim;
+  int32_t col[PAYNE_NPAR];        /* column in theta, or -1 if not sampled */
+  double  fixed[PAYNE_NPAR];      /* value used when col<0; NaN = absent (likelihood.py:51-55) */
+  int32_t n_poly;                 /* number of pc_k coefficients (0 = no continuum polynomial) */
+  int32_t poly_col[PAYNE_MAX_POLY];
+  int32_t spec_bool, phot_bool, modpoly_bool, photscale_bool;  /* runbools, fitstar.py:202-207 */
+  int32_t precision;              /* PAYNE_PREC_* */
+} PayneLayout;
+
+typedef struct PayneCtx PayneCtx;
+
+int payne_abi_version(void);
+const char* payne_last_error(void);
+
+/* spec / phot may be NULL when the corresponding runbool is 0. device = CUDA ordinal. */
+int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const PayneObs* obs,
+                     const PayneLayout* layout, int device, PayneCtx** out);
+void payne_ctx_destroy(PayneCtx* ctx);
+
+/* theta_dev: [B, ld] fp64 row-major on the device.  lnl_dev: [B] fp64. */
+int payne_lnlike_batch(PayneCtx* ctx, const double* theta_dev, int64_t B, int64_t ld,
+                       double* lnl_dev, void* stream);
+
+/* Same with HOST buffers: copies theta in, runs, copies lnL out, synchronises. */
+int payne_lnlike_batch_host(PayneCtx* ctx, const double* theta_host, int64_t B, int64_t ld,
+                            double* lnl_host);
+
+/* Model spectrum on the observed grid and magnitudes; either output may be NULL.
+ * flux_dev: [B, n_obs] fp64, mags_dev: [B, nb] fp64, lnl_dev: [B] fp64 or NULL. */
+int payne_model_batch(PayneCtx* ctx, const double* theta_dev, int64_t B, int64_t ld,
+                      double* flux_dev, double* mags_dev, double* lnl_dev, void* stream);
+
+/* Emulator forward pass only.  x_dev: [B, D_in] fp64 labels; y_dev: [B, ldy] fp32, ldy>=D_out. */
+int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, int64_t ldy,
+                   void* stream);
+
+/* Introspection for benches/tests: key is one of "n_ann","n_obs","nfft1","launches",
+ * "grid_loguniform","max_batch","sm_count". Returns the value or -1. */
+int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
+/* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points). */
+int payne_ctx_set(PayneCtx* ctx, const char* key, int64_t value);
+
+/* Per-kernel device time of the most recent payne_lnlike_batch call on this context,
+ * measured with CUDA events on the launching stream when timing is enabled
+ * (payne_ctx_set(ctx,"timing",1)).  which: 0 = emulator GEMM stages, 1 = fused tail,
+ * 2 = photometry.  Returns milliseconds, or a negative value if unavailable. */
+double payne_ctx_last_ms(PayneCtx* ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAYNE_B200_H */

@@ -1,0 +1,45 @@
+"""Build libpayne_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'csrc', 'payne_b200.cu')
+OUT = os.path.join(HERE, 'libpayne_b200.so')
+DEPS = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc'))] + \
+       [os.path.join(os.path.dirname(HERE), 'include', 'payne_b200.h')]
+
+
+def nvcc_path():
+    for c in [os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc']:
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError('nvcc not found')
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc_path(), '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+           '-Xcompiler', '-fPIC', '-shared', '-o', OUT, SRC]
+    if verbose:
+        cmd.insert(1, '-Xptxas')
+        cmd.insert(2, '-v')
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + r.stderr[-4000:])
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose='-v' in sys.argv))

@@ -1,0 +1,590 @@
+// C-ABI implementation: context creation (weights + per-dataset tables to HBM) and the
+// stream-ordered launch sequence  encode+lin1 -> lin2..lin6 -> photometry -> fused tail.
+// See include/payne_b200.h for the contract and the reference interfaces each entry replaces.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/payne_b200.h"
+#include "mlp_simt.cuh"
+#include "mlp_tc.cuh"
+#include "phot.cuh"
+#include "tail.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(PAYNE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+template <class T>
+int upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0) return PAYNE_OK;
+  CU_TRY(cudaMalloc((void**)dst, n * sizeof(T)));
+  CU_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return PAYNE_OK;
+}
+
+inline int ceil_log2(long long v) {
+  int l = 0;
+  while ((1LL << l) < v) ++l;
+  return l;
+}
+
+// np.linspace(a, b, n)
+std::vector<double> linspace(double a, double b, int n) {
+  std::vector<double> y(n);
+  const double step = (b - a) / (double)(n - 1);
+  for (int i = 0; i < n; ++i) y[i] = (double)i * step + a;
+  y[n - 1] = b;
+  return y;
+}
+
+// np.interp index/weight of x in the increasing grid xp (value = fp[j] + t (fp[j+1]-fp[j])).
+// outside: clamp (left=fp[0], right=fp[-1]) or NaN weight when nan_outside.
+void interp_entry(const std::vector<double>& xp, double x, bool nan_outside, int* j, float* t) {
+  const int n = (int)xp.size();
+  if (x < xp[0] || x > xp[n - 1]) {
+    if (nan_outside) { *j = 0; *t = std::numeric_limits<float>::quiet_NaN(); return; }
+    if (x < xp[0]) { *j = 0; *t = 0.f; } else { *j = n - 2; *t = 1.f; }
+    return;
+  }
+  if (x == xp[n - 1]) { *j = n - 2; *t = 1.f; return; }
+  int k = (int)(std::upper_bound(xp.begin(), xp.end(), x) - xp.begin()) - 1;   // xp[k] <= x < xp[k+1]
+  k = std::min(std::max(k, 0), n - 2);
+  *j = k;
+  *t = (float)((x - xp[k]) / (xp[k + 1] - xp[k]));
+}
+
+// sb(u) of smoothing.py:612-619 without the small-u cancellation
+double rot_sb(double u) {
+  u = std::fabs(u);
+  if (u < 0.5) {
+    // J1(u)/u = sum (-1)^m (u/2)^(2m) / (2 m! (m+1)!),  (3/(2u^2))(sin u/u - cos u) = 1.5 sum (-1)^(m+1) 2m u^(2m-2)/(2m+1)!
+    double a = 0.0, q = u * u, term1 = 0.5, term2 = 0.5;
+    // term1_m = (-1)^m (q/4)^m / (2 m!(m+1)!), term2_m = 1.5 (-1)^m (2m+2) q^m / (2m+3)!
+    for (int m = 0; m < 12; ++m) {
+      a += term1 + term2;
+      term1 *= -(q / 4.0) / ((double)(m + 1) * (double)(m + 2));
+      term2 *= -q * (double)(2 * m + 4) / ((double)(2 * m + 2) * (double)(2 * m + 4) * (double)(2 * m + 5));
+    }
+    return a;
+  }
+  return j1(u) / u - 3.0 * std::cos(u) / (2.0 * u * u) + 3.0 * std::sin(u) / (2.0 * u * u * u);
+}
+
+}  // namespace
+
+struct PayneCtx {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;   // used by the *_host entry
+  PayneLayout lay{};
+  // spectrum emulator
+  bool has_spec = false;
+  int D_in = 0, H[4] = {0, 0, 0, 0}, D_out = 0;   // H[0]=H1 (lin1,lin2 out), H[1]=H2, H[2]=H3
+  int dims_in[6], dims_out[6];
+  float* W[6] = {nullptr};
+  float* b[6] = {nullptr};
+  payne::TcWeights tcw[6];
+  payne::EncodeParams enc{};
+  payne::TailParams tail{};
+  size_t tail_smem = 0;
+  int tail_grid = 0;
+  int grid_loguniform = 0;
+  // photometry
+  bool has_phot = false;
+  payne::PhotParams phot{};
+  size_t phot_smem = 0;
+  // workspace
+  long long slab = 8192, slab_alloc = 0, ldf = 0;
+  float *flux = nullptr, *hA = nullptr, *hB = nullptr;
+  payne::TcActs actA, actB;
+  double* chi2_sed = nullptr;
+  int* status = nullptr;
+  // host staging
+  long long stage_cap = 0, stage_ld = 0;
+  double *theta_pin = nullptr, *lnl_pin = nullptr, *theta_stage = nullptr, *lnl_stage = nullptr;
+  // device allocations to free
+  std::vector<void*> owned;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double ms_acc[3] = {0, 0, 0};
+  bool ms_valid = false;
+  std::vector<std::array<cudaEvent_t, 4>> pending;
+  long long launches = 0;
+};
+
+namespace {
+
+template <class T>
+int upload_owned(PayneCtx* c, T** dst, const T* src, size_t n) {
+  int rc = upload(dst, src, n);
+  if (rc == PAYNE_OK && *dst) c->owned.push_back((void*)*dst);
+  return rc;
+}
+
+int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
+  using namespace payne;
+  c->D_in = s->D_in; c->H[0] = s->H1; c->H[1] = s->H2; c->H[2] = s->H3; c->D_out = s->D_out;
+  if (s->D_in < 1 || s->D_in > 8) return fail(PAYNE_E_INVALID, "D_in must be in [1,8]");
+  if (s->D_out < 32) return fail(PAYNE_E_INVALID, "D_out must be >= 32");
+  const int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
+  const int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
+  for (int k = 0; k < 6; ++k) {
+    c->dims_in[k] = din[k]; c->dims_out[k] = dout[k];
+    int rc = upload_owned(c, &c->W[k], s->W[k], (size_t)din[k] * dout[k]);
+    if (rc) return rc;
+    rc = upload_owned(c, &c->b[k], s->b[k], (size_t)dout[k]);
+    if (rc) return rc;
+  }
+  EncodeParams& E = c->enc;
+  E.D_in = s->D_in; E.H1 = s->H1; E.offset = s->encode_offset;
+  const int label_par[5] = {PAYNE_P_TEFF, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VMIC};
+  for (int i = 0; i < 8; ++i) {
+    E.col[i] = -1; E.fixed[i] = std::numeric_limits<double>::quiet_NaN(); E.xmin[i] = 0; E.xmax[i] = 1;
+  }
+  for (int i = 0; i < s->D_in; ++i) {
+    E.xmin[i] = s->xmin[i]; E.xmax[i] = s->xmax[i];
+    if (i < 5) { E.col[i] = c->lay.col[label_par[i]]; E.fixed[i] = c->lay.fixed[label_par[i]]; }
+  }
+
+  // ---- emulator grid
+  const int n = s->D_out;
+  std::vector<double> w(s->wavelength, s->wavelength + n), inv_dw(n - 1);
+  for (int i = 0; i + 1 < n; ++i) {
+    if (!(w[i + 1] > w[i])) return fail(PAYNE_E_INVALID, "wavelength grid must be strictly increasing");
+    inv_dw[i] = 1.0 / (w[i + 1] - w[i]);
+  }
+  TailParams& T = c->tail;
+  T.n = n;
+  double *dw, *dinv;
+  int rc = upload_owned(c, &dw, w.data(), n); if (rc) return rc;
+  rc = upload_owned(c, &dinv, inv_dw.data(), n - 1); if (rc) return rc;
+  T.w = dw; T.inv_dw = dinv;
+  T.lnw0 = std::log(w[0]);
+  T.inv_dlnw = (double)(n - 1) / (std::log(w[n - 1]) - std::log(w[0]));
+  T.sigma_in = kCkms / s->resolution;
+  // log-uniform check (informational; enables the analytic regrid fast path later)
+  double maxdev = 0.0;
+  for (int i = 0; i < n; ++i)
+    maxdev = std::max(maxdev, std::fabs((std::log(w[i]) - T.lnw0) * T.inv_dlnw - (double)i));
+  c->grid_loguniform = maxdev < 1e-7;
+
+  // ---- stage 1 (rotation) regrid: smoothing.py:649-668, 306-314
+  const int l2 = ceil_log2(n);
+  const int N1 = 1 << l2;
+  T.log2N1 = l2;
+  std::vector<double> x1 = linspace(std::log(w[0]), std::log(w[n - 1]), N1);
+  for (auto& v : x1) v = std::exp(v);
+  std::vector<int2> fwd(N1), back(n);
+  for (int k = 0; k < N1; ++k) {
+    int j; float t;
+    interp_entry(w, x1[k], false, &j, &t);
+    fwd[k] = make_int2(j, 0);
+    std::memcpy(&fwd[k].y, &t, 4);
+  }
+  for (int i = 0; i < n; ++i) {
+    int k; float t;
+    interp_entry(x1, w[i], true, &k, &t);
+    back[i] = make_int2(k, 0);
+    std::memcpy(&back[i].y, &t, 4);
+  }
+  std::vector<double> dl(N1 - 1);
+  for (int k = 0; k + 1 < N1; ++k) dl[k] = std::log(x1[k + 1]) - std::log(x1[k]);
+  std::nth_element(dl.begin(), dl.begin() + (N1 - 1) / 2, dl.end());
+  const double dv1 = kCkms * dl[(N1 - 1) / 2];          // odd count -> the middle element
+  int2 *dfwd, *dback;
+  rc = upload_owned(c, &dfwd, fwd.data(), N1); if (rc) return rc;
+  rc = upload_owned(c, &dback, back.data(), n); if (rc) return rc;
+  T.fwd1 = dfwd; T.back1 = dback;
+  // rotational transfer function table
+  const double h = 1.0 / 32.0;
+  const double vmax = 600.0;
+  long long ntab = (long long)std::ceil(3.14159265358979323846 * vmax / dv1 / h) + 8;
+  ntab = std::min<long long>(ntab, 1LL << 21);
+  std::vector<float> sbt(ntab + 3);
+  for (long long i = 0; i < ntab + 3; ++i) sbt[i] = (float)rot_sb((double)(i - 1) * h);
+  float* dsb;
+  rc = upload_owned(c, &dsb, sbt.data(), sbt.size()); if (rc) return rc;
+  T.sbtab = dsb; T.ntab = (int)ntab; T.sb_h = h;
+  T.sb_scale = 2.0 * 3.14159265358979323846 / ((double)N1 * dv1) / h;
+  // twiddles
+  std::vector<float2> tw(N1 / 2);
+  for (int e = 0; e < N1 / 2; ++e) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)e / (double)N1;
+    tw[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  float2* dtw;
+  rc = upload_owned(c, &dtw, tw.data(), tw.size()); if (rc) return rc;
+  T.tw = dtw; T.log2tw = l2; T.max_log2N = l2;
+  c->tail_smem = (size_t)4 * N1;
+  if (c->tail_smem > 227 * 1024 - 2048)
+    return fail(PAYNE_E_UNSUPPORTED, "emulator grid needs an FFT larger than one SM's shared memory");
+
+  // ---- observation
+  const int no = obs->n_obs;
+  if (no < 1) return fail(PAYNE_E_INVALID, "n_obs must be >= 1");
+  std::vector<double> ow(obs->wave, obs->wave + no), lnw(no), ot(no), inv_s(no), ox(no);
+  const double omin = *std::min_element(ow.begin(), ow.end());
+  const double omax = *std::max_element(ow.begin(), ow.end());
+  for (int j = 0; j < no; ++j) {
+    lnw[j] = std::log(ow[j]);
+    inv_s[j] = 1.0 / obs->eflux[j];
+    ot[j] = obs->flux[j] / obs->eflux[j];
+    const double x = ow[j] - omin;                     // fitutils.py:13-14
+    ox[j] = 2.0 * (x / (omax - omin)) - 1.0;
+  }
+  double *d1, *d2, *d3, *d4, *d5;
+  rc = upload_owned(c, &d1, ow.data(), no); if (rc) return rc;
+  rc = upload_owned(c, &d2, lnw.data(), no); if (rc) return rc;
+  rc = upload_owned(c, &d3, ot.data(), no); if (rc) return rc;
+  rc = upload_owned(c, &d4, inv_s.data(), no); if (rc) return rc;
+  rc = upload_owned(c, &d5, ox.data(), no); if (rc) return rc;
+  T.n_obs = no; T.obs_w = d1; T.obs_lnw = d2; T.obs_ot = d3; T.obs_inv_s = d4; T.obs_x = d5;
+  T.obs_min = omin; T.obs_max = omax;
+  for (int i = 0; i < PAYNE_NPAR; ++i) { T.col[i] = c->lay.col[i]; T.fixed[i] = c->lay.fixed[i]; }
+  T.n_poly = c->lay.modpoly_bool ? c->lay.n_poly : 0;
+  for (int i = 0; i < PAYNE_MAX_POLY; ++i) T.poly_col[i] = c->lay.poly_col[i];
+  c->ldf = ((long long)n + 3) / 4 * 4;
+
+  CU_TRY(cudaFuncSetAttribute(payne::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->tail_smem));
+  int occ = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_kernel, payne::kTailThreads,
+                                                       c->tail_smem));
+  if (occ < 1) return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
+  c->tail_grid = occ * c->sm_count;
+  // tensor-core operand copies of the weights
+  for (int k = 1; k < 6; ++k) {
+    rc = payne::tc_prepare_weights(&c->tcw[k], c->W[k], dout[k], din[k], &c->owned);
+    if (rc) return fail(rc, "tc_prepare_weights failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
+  }
+  return PAYNE_OK;
+}
+
+int build_phot(PayneCtx* c, const PaynePhotNet* p, const PayneObs* obs) {
+  using namespace payne;
+  if (p->nb != obs->nb) return fail(PAYNE_E_INVALID, "photometry net and observation disagree on nb");
+  const int nb = p->nb, H = p->H;
+  PhotParams& P = c->phot;
+  P.nb = nb; P.H = H;
+  std::vector<float> w2t((size_t)nb * H * H);
+  for (int b = 0; b < nb; ++b)
+    for (int ho = 0; ho < H; ++ho)
+      for (int hi = 0; hi < H; ++hi)
+        w2t[((size_t)b * H + hi) * H + ho] = p->w2[((size_t)b * H + ho) * H + hi];
+  float *d1, *d2, *d3, *d4, *d5, *d6;
+  int rc;
+  rc = upload_owned(c, &d1, p->w1, (size_t)nb * H * 6); if (rc) return rc;
+  rc = upload_owned(c, &d2, p->b1, (size_t)nb * H); if (rc) return rc;
+  rc = upload_owned(c, &d3, w2t.data(), w2t.size()); if (rc) return rc;
+  rc = upload_owned(c, &d4, p->b2, (size_t)nb * H); if (rc) return rc;
+  rc = upload_owned(c, &d5, p->w3, (size_t)nb * H); if (rc) return rc;
+  rc = upload_owned(c, &d6, p->b3, (size_t)nb); if (rc) return rc;
+  P.w1 = d1; P.b1 = d2; P.w2t = d3; P.b2 = d4; P.w3 = d5; P.b3 = d6;
+  for (int i = 0; i < 6; ++i) { P.xmin[i] = p->xmin[i]; P.xmax[i] = p->xmax[i]; }
+  double *h1, *h2, *h3;
+  rc = upload_owned(c, &h1, p->hiav, (size_t)nb * 5); if (rc) return rc;
+  rc = upload_owned(c, &h2, obs->phot_mag, (size_t)nb); if (rc) return rc;
+  rc = upload_owned(c, &h3, obs->phot_err, (size_t)nb); if (rc) return rc;
+  P.hiav = h1; P.obs_mag = h2; P.obs_err = h3;
+  for (int i = 0; i < PAYNE_NPAR; ++i) { P.col[i] = c->lay.col[i]; P.fixed[i] = c->lay.fixed[i]; }
+  P.photscale = c->lay.photscale_bool;
+  c->phot_smem = (size_t)2 * kPhotTile * H * sizeof(double);
+  if (c->phot_smem > 200 * 1024) return fail(PAYNE_E_UNSUPPORTED, "photometry hidden width too large");
+  CU_TRY(cudaFuncSetAttribute(payne::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->phot_smem));
+  return PAYNE_OK;
+}
+
+int ensure_workspace(PayneCtx* c, long long B) {
+  const long long need = std::min(B, c->slab);
+  if (need <= c->slab_alloc) return PAYNE_OK;
+  auto drop = [&](void* p) { if (p) cudaFree(p); };
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed);
+  payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
+  c->flux = c->hA = c->hB = nullptr; c->chi2_sed = nullptr; c->slab_alloc = 0;
+  const long long rows = (need + 127) / 128 * 128;
+  if (c->has_spec) {
+    const long long hmax = std::max({c->H[0], c->H[1], c->H[2]});
+    CU_TRY(cudaMalloc((void**)&c->flux, (size_t)rows * c->ldf * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
+    int rc = payne::tc_alloc_acts(&c->actA, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+    rc = payne::tc_alloc_acts(&c->actB, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+  }
+  CU_TRY(cudaMalloc((void**)&c->chi2_sed, (size_t)rows * sizeof(double)));
+  c->slab_alloc = need;
+  return PAYNE_OK;
+}
+
+// emulator forward for `nb` rows: labels gathered from x (ld) by E -> out [nb, ldo] fp32
+int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long long ld, int nb,
+            float* out, long long ldo, cudaStream_t st) {
+  using namespace payne;
+  const int prec = c->lay.precision;
+  {
+    const long long tot = (long long)nb * c->H[0];
+    encode_layer1_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, x, ld, c->W[0], c->b[0], c->hA,
+                                                                         c->H[0], nb);
+    c->launches++;
+  }
+  if (prec == PAYNE_PREC_SIMT_FP32) {
+    float* cur = c->hA; float* nxt = c->hB;
+    for (int k = 1; k < 6; ++k) {
+      const int K = c->dims_in[k], N = c->dims_out[k];
+      dim3 grid((N + 127) / 128, (nb + 127) / 128);
+      if (k < 5) {
+        sgemm_bias_act_kernel<true><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K);
+        std::swap(cur, nxt);
+      } else {
+        sgemm_bias_act_kernel<false><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K);
+      }
+      c->launches++;
+    }
+  } else {
+    int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, c->hA, &c->actA, &c->actB, nb, out, ldo,
+                           prec, c->sm_count, st, &c->launches);
+    if (rc) return fail(rc, "tensor-core MLP path failed (precision " + std::to_string(prec) + ")");
+  }
+  CU_TRY(cudaGetLastError());
+  return PAYNE_OK;
+}
+
+int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, double* flux_out,
+              double* mags_out, double* lnl, cudaStream_t st) {
+  using namespace payne;
+  if (B <= 0) return PAYNE_OK;
+  if (ld < c->lay.ndim) return fail(PAYNE_E_INVALID, "ld < ndim");
+  CU_TRY(cudaSetDevice(c->device));
+  int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  if (c->timing) { c->ms_acc[0] = c->ms_acc[1] = c->ms_acc[2] = 0; c->ms_valid = false; c->pending.clear(); }
+  for (long long p0 = 0; p0 < B; p0 += c->slab) {
+    const int nb = (int)std::min(c->slab, B - p0);
+    const double* th = theta + p0 * ld;
+    std::array<cudaEvent_t, 4> evs{};
+    if (c->timing) {
+      for (auto& e : evs) CU_TRY(cudaEventCreate(&e));
+      CU_TRY(cudaEventRecord(evs[0], st));
+    }
+    if (c->has_spec) {
+      rc = run_mlp(c, c->enc, th, ld, nb, c->flux, c->ldf, st);
+      if (rc) return rc;
+    }
+    if (c->timing) CU_TRY(cudaEventRecord(evs[1], st));
+    if (c->has_phot) {
+      PhotParams P = c->phot;
+      P.theta = th; P.ld = ld; P.B = nb; P.chi2_sed = c->chi2_sed;
+      P.mags_out = mags_out ? mags_out + p0 * P.nb : nullptr;
+      phot_kernel<<<(nb + kPhotTile - 1) / kPhotTile, kPhotThreads, c->phot_smem, st>>>(P);
+      c->launches++;
+    }
+    if (c->timing) CU_TRY(cudaEventRecord(evs[2], st));
+    if (c->has_spec) {
+      TailParams T = c->tail;
+      T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb;
+      T.chi2_sed = c->has_phot ? c->chi2_sed : nullptr;
+      T.lnl = lnl ? lnl + p0 : nullptr;
+      T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
+      T.status = c->status;
+      tail_kernel<<<std::min(c->tail_grid, nb), kTailThreads, c->tail_smem, st>>>(T);
+      c->launches++;
+    } else if (lnl) {
+      lnl_from_sed_kernel<<<(nb + 255) / 256, 256, 0, st>>>(c->chi2_sed, lnl + p0, nb);
+      c->launches++;
+    }
+    if (c->timing) { CU_TRY(cudaEventRecord(evs[3], st)); c->pending.push_back(evs); }
+    CU_TRY(cudaGetLastError());
+  }
+  return PAYNE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int payne_abi_version(void) { return PAYNE_ABI_VERSION; }
+const char* payne_last_error(void) { return g_err.c_str(); }
+
+int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const PayneObs* obs,
+                     const PayneLayout* layout, int device, PayneCtx** out) {
+  if (!out || !layout || !obs) return fail(PAYNE_E_INVALID, "null argument");
+  *out = nullptr;
+  if (layout->spec_bool && !spec) return fail(PAYNE_E_INVALID, "spec_bool set but no spectrum net");
+  if (layout->phot_bool && !phot) return fail(PAYNE_E_INVALID, "phot_bool set but no photometry net");
+  if (!layout->spec_bool && !layout->phot_bool) return fail(PAYNE_E_INVALID, "nothing to fit");
+  if (layout->n_poly < 0 || layout->n_poly > PAYNE_MAX_POLY) return fail(PAYNE_E_INVALID, "n_poly out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PAYNE_E_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(PAYNE_E_INVALID, "bad device ordinal");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(PAYNE_E_UNSUPPORTED, "built for sm_100a (B200) only");
+  PayneCtx* c = new PayneCtx();
+  c->device = device; c->sm_count = prop.multiProcessorCount; c->lay = *layout;
+  c->has_spec = layout->spec_bool != 0; c->has_phot = layout->phot_bool != 0;
+  int rc = PAYNE_OK;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(PAYNE_E_CUDA, "stream");
+  if (!rc && cudaMalloc((void**)&c->status, sizeof(int)) != cudaSuccess) rc = fail(PAYNE_E_NOMEM, "status");
+  if (!rc) cudaMemset(c->status, 0, sizeof(int));
+  if (!rc && c->has_spec) rc = build_spec(c, spec, obs);
+  if (!rc && c->has_phot) rc = build_phot(c, phot, obs);
+  if (rc) { std::string keep = g_err; payne_ctx_destroy(c); g_err = keep; return rc; }
+  *out = c;
+  return PAYNE_OK;
+}
+
+void payne_ctx_destroy(PayneCtx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->owned) cudaFree(p);
+  auto drop = [&](void* p) { if (p) cudaFree(p); };
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->status);
+  payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
+  drop(c->theta_stage); drop(c->lnl_stage);
+  if (c->theta_pin) cudaFreeHost(c->theta_pin);
+  if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
+  for (auto& evs : c->pending) for (auto e : evs) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int payne_lnlike_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t ld, double* lnl_dev,
+                       void* stream) {
+  if (!c || !theta_dev || !lnl_dev) return fail(PAYNE_E_INVALID, "null argument");
+  return run_batch(c, theta_dev, B, ld, nullptr, nullptr, lnl_dev, (cudaStream_t)stream);
+}
+
+int payne_model_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t ld, double* flux_dev,
+                      double* mags_dev, double* lnl_dev, void* stream) {
+  if (!c || !theta_dev) return fail(PAYNE_E_INVALID, "null argument");
+  return run_batch(c, theta_dev, B, ld, flux_dev, mags_dev, lnl_dev, (cudaStream_t)stream);
+}
+
+int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, int64_t ld, double* lnl_host) {
+  if (!c || !theta_host || !lnl_host) return fail(PAYNE_E_INVALID, "null argument");
+  if (B <= 0) return PAYNE_OK;
+  CU_TRY(cudaSetDevice(c->device));
+  if (B > c->stage_cap || ld != c->stage_ld) {
+    if (c->theta_pin) cudaFreeHost(c->theta_pin);
+    if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
+    if (c->theta_stage) cudaFree(c->theta_stage);
+    if (c->lnl_stage) cudaFree(c->lnl_stage);
+    c->theta_pin = c->lnl_pin = c->theta_stage = c->lnl_stage = nullptr; c->stage_cap = 0;
+    CU_TRY(cudaMallocHost((void**)&c->theta_pin, (size_t)B * ld * sizeof(double)));
+    CU_TRY(cudaMallocHost((void**)&c->lnl_pin, (size_t)B * sizeof(double)));
+    CU_TRY(cudaMalloc((void**)&c->theta_stage, (size_t)B * ld * sizeof(double)));
+    CU_TRY(cudaMalloc((void**)&c->lnl_stage, (size_t)B * sizeof(double)));
+    c->stage_cap = B; c->stage_ld = ld;
+  }
+  std::memcpy(c->theta_pin, theta_host, (size_t)B * ld * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(c->theta_stage, c->theta_pin, (size_t)B * ld * sizeof(double),
+                         cudaMemcpyHostToDevice, c->stream));
+  int rc = run_batch(c, c->theta_stage, B, ld, nullptr, nullptr, c->lnl_stage, c->stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(c->lnl_pin, c->lnl_stage, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  std::memcpy(lnl_host, c->lnl_pin, (size_t)B * sizeof(double));
+  return PAYNE_OK;
+}
+
+int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, int64_t ldy, void* stream) {
+  if (!c || !x_dev || !y_dev) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
+  if (ldy < c->D_out) return fail(PAYNE_E_INVALID, "ldy < D_out");
+  if (B <= 0) return PAYNE_OK;
+  CU_TRY(cudaSetDevice(c->device));
+  int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  payne::EncodeParams E = c->enc;
+  for (int i = 0; i < E.D_in; ++i) E.col[i] = i;
+  for (long long p0 = 0; p0 < B; p0 += c->slab) {
+    const int nb = (int)std::min<long long>(c->slab, B - p0);
+    rc = run_mlp(c, E, x_dev + p0 * c->D_in, c->D_in, nb, y_dev + p0 * ldy, ldy, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return PAYNE_OK;
+}
+
+int64_t payne_ctx_query(PayneCtx* c, const char* key) {
+  if (!c || !key) return -1;
+  std::string k(key);
+  if (k == "n_ann") return c->D_out;
+  if (k == "n_obs") return c->tail.n_obs;
+  if (k == "nfft1") return c->has_spec ? (1LL << c->tail.log2N1) : 0;
+  if (k == "launches") return c->launches;
+  if (k == "grid_loguniform") return c->grid_loguniform;
+  if (k == "max_batch") return c->slab;
+  if (k == "sm_count") return c->sm_count;
+  if (k == "tail_grid") return c->tail_grid;
+  if (k == "precision") return c->lay.precision;
+  if (k == "status") {
+    int v = 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, c->status, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
+  }
+  return -1;
+}
+
+int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
+  if (!c || !key) return fail(PAYNE_E_INVALID, "null argument");
+  std::string k(key);
+  if (k == "precision") {
+    if (value < 0 || value > 3) return fail(PAYNE_E_INVALID, "unknown precision");
+    c->lay.precision = (int)value;
+    return PAYNE_OK;
+  }
+  if (k == "max_batch") {
+    if (value < 1) return fail(PAYNE_E_INVALID, "max_batch must be positive");
+    c->slab = value;
+    return PAYNE_OK;
+  }
+  if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
+  return fail(PAYNE_E_INVALID, "unknown key " + k);
+}
+
+double payne_ctx_last_ms(PayneCtx* c, int which) {
+  if (!c || which < 0 || which > 2 || !c->timing) return -1.0;
+  if (!c->ms_valid) {
+    for (auto& evs : c->pending) {
+      if (cudaEventSynchronize(evs[3]) != cudaSuccess) return -1.0;
+      for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+        c->ms_acc[i == 0 ? 0 : (i == 1 ? 2 : 1)] += ms;   // [mlp, phot, tail] -> which {0,2,1}
+      }
+      for (auto e : evs) cudaEventDestroy(e);
+    }
+    c->pending.clear();
+    c->ms_valid = true;
+  }
+  return c->ms_acc[which];
+}
+
+}  // extern "C"

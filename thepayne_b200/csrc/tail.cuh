@@ -1,0 +1,357 @@
+// Fused tail of the likelihood: emulator flux row -> rotational broadening -> Doppler shift ->
+// instrumental broadening -> resample onto the observed pixels -> Chebyshev continuum -> chi2.
+// One CTA owns one live point at a time; the only HBM/L2 traffic per point is the fp32 flux
+// row (read once, rewritten in place after the rotational stage) plus per-dataset tables.
+//
+// Reference semantics reproduced step by step (paths relative to the reference checkout):
+//   Payne/predict/predictspec.py:228-289   getspec: vsini -> edge patch -> Doppler -> inst_R / interp
+//   Payne/utils/smoothing.py:132-143       mask_wave (+-20 sigma, strict), nan_to_num(nan=1)
+//   Payne/utils/smoothing.py:649-668       resample_wave: 2^k uniform ln-lambda regrid by np.interp
+//   Payne/utils/smoothing.py:293-314,610-629  rotational kernel in Fourier space, np.interp back
+//   Payne/utils/smoothing.py:252-291,588-608  Gaussian taper, np.interp onto outwave (NaN outside)
+//   Payne/fitting/fitutils.py:11-20        polycalc (chebval on the normalised observed grid)
+//   Payne/fitting/likelihood.py:95-97,117  chi2 and lnL
+//
+// Numerics: wavelength / index arithmetic in fp64, flux arithmetic in fp32 on the line depth
+// d = f - 1 (both transfer functions have unit DC gain, so the FFTs only see the ~0.1-amplitude
+// depth signal), residuals and the chi2 sum in fp64.
+#pragma once
+#include <math_constants.h>
+#include "fft.cuh"
+#include "../../include/payne_b200.h"
+
+namespace payne {
+
+constexpr double kCkms = 2.998e5;               // smoothing.py:16
+constexpr double kSpeedOfLight = 299792.458;    // predictspec.py:12
+constexpr double kFwhmFit = 2.355;              // genmod.py:83
+constexpr int kTailThreads = 256;
+
+struct TailParams {
+  // emulator grid
+  int n;
+  const double* w;        // [n]
+  const double* inv_dw;   // [n-1] 1/(w[j+1]-w[j])
+  double lnw0, inv_dlnw;  // index guess: (ln x - lnw0) * inv_dlnw
+  double sigma_in;        // ckms / ANN.resolution  (smoothing.py:113)
+  // stage 1 (rotation): per-dataset regrid tables, np.interp semantics baked in on the host
+  int log2N1;
+  const int2* fwd1;       // [N1]  {j, bits(t)}: g_k = f[j] + t (f[j+1]-f[j])
+  const int2* back1;      // [n]   {k, bits(t)}: f_i = g[k] + t (g[k+1]-g[k])
+  double sb_scale;        // 2 pi / (N1 dv1 h): table coordinate of bin k is |vsini| k sb_scale
+  double sb_h;            // table spacing in u
+  const float* sbtab;     // sb(u) at u = (i-1) h, i in [0, ntab+3)
+  int ntab;
+  // twiddles exp(-2 pi i e / Ntw), e < Ntw/2
+  const float2* tw;
+  int log2tw;
+  int max_log2N;          // largest FFT the shared-memory carve-out holds
+  // observation
+  int n_obs;
+  const double* obs_w;      // [n_obs] wavelength
+  const double* obs_lnw;    // [n_obs] ln wavelength
+  const double* obs_ot;     // [n_obs] flux / eflux
+  const double* obs_inv_s;  // [n_obs] 1 / eflux
+  const double* obs_x;      // [n_obs] Chebyshev abscissa (fitutils.py:13-14)
+  double obs_min, obs_max;
+  // parameter layout
+  int col[PAYNE_NPAR];
+  double fixed[PAYNE_NPAR];
+  int n_poly;
+  int poly_col[PAYNE_MAX_POLY];
+  // batch
+  const double* theta;
+  long long ld;
+  float* flux;              // [B, ldf] emulator output; scratch, overwritten
+  long long ldf;
+  const double* chi2_sed;   // [B] or null
+  double* lnl;              // [B] or null
+  double* model_out;        // [B, n_obs] or null
+  int* status;              // device flag: bit0 = a point needed a larger FFT than the carve-out
+  int B;
+};
+
+struct PointSetup {
+  double vsini_scale;   // |vsini| * sb_scale
+  double D;             // Doppler factor
+  double u0, inv_du;    // resampled grid of stage 2 (observed frame)
+  double x0t, rho;      // rest-frame grid point of thread tid and ratio per kTailThreads steps
+  double du, rM;
+  double lnD, u0t;      // u0t = ln w[i0] in the rest frame
+  double poly[PAYNE_MAX_POLY];
+  float taper_a;        // exp(-a k^2)
+  float hdu;
+  int do_rot, use_inst, bad, i0, i1, log2N2;
+};
+
+__device__ __forceinline__ double get_par(const TailParams& P, const double* th, int which) {
+  return P.col[which] >= 0 ? th[P.col[which]] : P.fixed[which];
+}
+
+__device__ __forceinline__ int zidx(int k) { return 2 * swz(k >> 1) + (k & 1); }
+
+// largest j in [lo, hi] with w[j]*D <= x, assuming w[lo]*D <= x; starts from a guess.
+__device__ __forceinline__ int locate(const double* __restrict__ w, double D, double x, int guess,
+                                      int lo, int hi) {
+  int j = min(max(guess, lo), hi);
+  int steps = 0;
+  while (j > lo && x < __ldg(w + j) * D && steps < 4) { --j; ++steps; }
+  while (j < hi && x >= __ldg(w + j + 1) * D && steps < 8) { ++j; ++steps; }
+  if (steps >= 4) {  // far-off guess (irregular grid): bisection
+    int a = lo, b = hi;
+    if (x < __ldg(w + a) * D) return a;
+    while (b > a) {
+      int mid = (a + b + 1) >> 1;
+      if (__ldg(w + mid) * D <= x) a = mid; else b = mid - 1;
+    }
+    j = a;
+  }
+  return j;
+}
+
+// Rotational transfer function sb(u) (smoothing.py:612-619) from a 4-point Lagrange table.
+struct RotH {
+  const float* __restrict__ tab;
+  double scale;     // table coordinate per bin
+  double h;
+  float invM;
+  int ntab;
+  __device__ __forceinline__ float operator()(int k) const {
+    const double xt = scale * (double)k;
+    const int i = (int)xt;
+    if (i + 2 >= ntab) return direct(xt * h) * invM;
+    const float f = (float)(xt - (double)i);
+    const float* t = tab + i;  // t[0] = sb((i-1) h)
+    const float fm1 = f - 1.f, fm2 = f - 2.f, fp1 = f + 1.f;
+    const float wm = -f * fm1 * fm2 * (1.f / 6.f);
+    const float w0 = fp1 * fm1 * fm2 * 0.5f;
+    const float w1 = -fp1 * f * fm2 * 0.5f;
+    const float w2 = fp1 * f * fm1 * (1.f / 6.f);
+    return (wm * __ldg(t) + w0 * __ldg(t + 1) + w1 * __ldg(t + 2) + w2 * __ldg(t + 3)) * invM;
+  }
+  static __device__ __noinline__ float direct(double u) {  // beyond the table: fp64 closed form
+    if (u == 0.0) return 1.f;
+    double s, c;
+    sincos(u, &s, &c);
+    return (float)(j1(u) / u - 3.0 * c / (2.0 * u * u) + 3.0 * s / (2.0 * u * u * u));
+  }
+};
+
+// Gaussian taper exp(-2 pi^2 sigma^2 ss^2) (smoothing.py:598-600), ss = k / (N dv).
+struct GaussH {
+  float a, invM;
+  __device__ __forceinline__ float operator()(int k) const {
+    const float kf = (float)k;
+    return expf(-a * kf * kf) * invM;
+  }
+};
+
+__device__ __forceinline__ double chebval_dev(double x, const double* c, int nc) {
+  // numpy.polynomial.chebyshev.chebval (Clenshaw), same operation order
+  if (nc == 1) return c[0];
+  if (nc == 2) return c[0] + c[1] * x;
+  const double x2 = 2.0 * x;
+  double c0 = c[nc - 2], c1 = c[nc - 1];
+  for (int i = 3; i <= nc; ++i) {
+    const double tmp = c0;
+    c0 = c[nc - i] - c1;
+    c1 = tmp + c1 * x2;
+  }
+  return c0 + c1 * x;
+}
+
+__device__ __forceinline__ float depth_of(float v, bool is_depth, bool fill_nan) {
+  if (is_depth) return v;
+  if (fill_nan && v != v) return 0.f;   // nan_to_num(nan=1.0) (smoothing.py:138) in depth space
+  return v - 1.f;
+}
+
+__device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S) {
+  const double vrot = get_par(P, th, PAYNE_P_VROT);
+  const double vrad = get_par(P, th, PAYNE_P_VRAD);
+  const double instR = get_par(P, th, PAYNE_P_INSTR);
+  S.bad = 0;
+  S.do_rot = (vrot != 0.0);                       // predictspec.py:231 (NaN != 0 is true)
+  if (vrot != vrot) S.bad = 1;                    // NaN kernel -> NaN spectrum
+  S.vsini_scale = fabs(vrot) * P.sb_scale;        // sigma = sqrt(vsini^2 - 0) (smoothing.py:297)
+  S.D = (vrad != 0.0) ? 1.0 + (vrad / kSpeedOfLight) : 1.0;   // predictspec.py:245-249
+  if (!(S.D > 0.0)) S.bad = 1;
+  S.lnD = log(S.D);
+  for (int k = 0; k < P.n_poly; ++k) S.poly[k] = th[P.poly_col[k]];
+  const double Rs = kFwhmFit * instR;             // genmod.py:83
+  S.use_inst = (Rs > 0.0);                        // predictspec.py:257 (false for NaN)
+  S.log2N2 = 0; S.i0 = 0; S.i1 = P.n - 1;
+  if (!S.use_inst || S.bad) return;
+  // mask_wave (smoothing.py:631-647): wlim * (1 + 20/width * [-1, 1]), strict inequalities
+  const double lo = P.obs_min * (1.0 + 20.0 / Rs * -1.0);
+  const double hi = P.obs_max * (1.0 + 20.0 / Rs * 1.0);
+  const int n = P.n;
+  // first index with w*D > lo
+  int g0 = (int)ceil((log(lo) - S.lnD - P.lnw0) * P.inv_dlnw);
+  int i0;
+  if (!(__ldg(P.w + n - 1) * S.D > lo)) i0 = n;
+  else if (__ldg(P.w) * S.D > lo) i0 = 0;
+  else i0 = locate(P.w, S.D, lo, g0, 0, n - 2) + 1;   // locate: last with w*D <= lo
+  // last index with w*D < hi
+  int i1;
+  if (!(__ldg(P.w) * S.D < hi)) i1 = -1;
+  else if (__ldg(P.w + n - 1) * S.D < hi) i1 = n - 1;
+  else {
+    int g1 = (int)floor((log(hi) - S.lnD - P.lnw0) * P.inv_dlnw);
+    i1 = locate(P.w, S.D, hi, g1, 0, n - 2);          // last with w*D <= hi
+    if (__ldg(P.w + i1) * S.D == hi) --i1;              // strict
+  }
+  const int nM = i1 - i0 + 1;
+  if (nM < 17) { S.bad = 1; return; }
+  int l2 = 32 - __clz(nM - 1);                     // ceil(log2(nM))
+  if (l2 > P.max_log2N) { S.bad = 2; atomicOr(P.status, 1); return; }
+  S.i0 = i0; S.i1 = i1; S.log2N2 = l2;
+  const int N2 = 1 << l2;
+  const double u0 = log(__ldg(P.w + i0) * S.D), u1 = log(__ldg(P.w + i1) * S.D);
+  S.du = (u1 - u0) / (double)(N2 - 1);             // np.linspace step
+  S.u0 = u0;
+  S.u0t = log(__ldg(P.w + i0));
+  S.inv_du = 1.0 / S.du;
+  S.hdu = (float)(0.5 * S.du);
+  S.rM = (double)(nM - 1) / (double)(N2 - 1);
+  S.rho = exp(S.du * (double)kTailThreads);
+  const double sig_out = kCkms / Rs;               // smoothing.py:106
+  const double s2 = sig_out * sig_out - P.sigma_in * P.sigma_in;   // smoothing.py:271
+  if (!(s2 >= 0.0)) { S.bad = 1; return; }         // sqrt(<0) = NaN everywhere
+  const double dv = kCkms * S.du;                  // smoothing.py:282
+  const double nd = (double)N2 * dv;
+  S.taper_a = (float)(2.0 * CUDART_PI * CUDART_PI * s2 / (nd * nd));
+}
+
+__global__ void __launch_bounds__(kTailThreads, 3)
+tail_kernel(const __grid_constant__ TailParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float* zf = reinterpret_cast<float*>(smem_raw);
+  __shared__ PointSetup S;
+  __shared__ double red[kTailThreads / 32];
+  const int tid = threadIdx.x;
+  const Twiddles tw{P.tw, P.log2tw};
+  const double nan = CUDART_NAN;
+
+  for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
+    const double* th = P.theta + (long long)p * P.ld;
+    float* row = P.flux + (long long)p * P.ldf;
+    if (tid == 0) tail_setup(P, th, S);
+    __syncthreads();
+    if (S.bad) {
+      if (P.model_out)
+        for (int j = tid; j < P.n_obs; j += kTailThreads) P.model_out[(long long)p * P.n_obs + j] = nan;
+      if (tid == 0 && P.lnl) P.lnl[p] = nan;
+      __syncthreads();
+      continue;
+    }
+    bool is_depth = false;
+
+    // ---------------- stage 1: rotational broadening on the full emulator grid
+    if (S.do_rot) {
+      const int N1 = 1 << P.log2N1, log2M = P.log2N1 - 1;
+      for (int k = tid; k < N1; k += kTailThreads) {
+        const int2 e = __ldg(P.fwd1 + k);
+        const float t = __int_as_float(e.y);
+        const float a = depth_of(row[e.x], false, true), b = depth_of(row[e.x + 1], false, true);
+        zf[zidx(k)] = a + t * (b - a);
+      }
+      __syncthreads();
+      FftPlan plan; plan.make(log2M);
+      fft_forward(z, log2M, plan, tw, tid, kTailThreads);
+      RotH H{P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(1 << log2M), P.ntab};
+      filter_pairs(z, log2M, plan, tw, H, tid, kTailThreads);
+      fft_inverse(z, log2M, plan, tw, tid, kTailThreads);
+      // back onto the emulator grid + the edge patch of predictspec.py:240-241
+      const int n = P.n;
+      for (int i = tid; i < n; i += kTailThreads) {
+        if (i == 0 || i == n - 1) continue;
+        const int2 e = __ldg(P.back1 + i);
+        const float t = __int_as_float(e.y);
+        const float g0 = zf[zidx(e.x)], g1 = zf[zidx(e.x + 1)];
+        const float v = g0 + t * (g1 - g0);      // t = NaN marks "outside" (smoothing.py:313-314)
+        row[i] = v;
+        if (i == 1) row[0] = v;
+        if (i == n - 2) row[n - 1] = v;
+      }
+      is_depth = true;
+      __syncthreads();
+    }
+
+    double acc = 0.0;
+    if (S.use_inst) {
+      // ---------------- stage 2: mask, regrid, Gaussian broadening
+      const int N2 = 1 << S.log2N2, log2M = S.log2N2 - 1;
+      const int i0 = S.i0, i1 = S.i1;
+      double xt = exp(S.u0t + S.du * (double)tid);   // rest-frame grid point
+      for (int k = tid; k < N2; k += kTailThreads, xt *= S.rho) {
+        int j = locate(P.w, 1.0, xt, i0 + (int)((double)k * S.rM), i0, i1 - 1);
+        double t = (xt - __ldg(P.w + j)) * __ldg(P.inv_dw + j);
+        t = fmin(fmax(t, 0.0), 1.0);
+        const float a = depth_of(row[j], is_depth, true), b = depth_of(row[j + 1], is_depth, true);
+        zf[zidx(k)] = a + (float)t * (b - a);
+      }
+      __syncthreads();
+      FftPlan plan; plan.make(log2M);
+      fft_forward(z, log2M, plan, tw, tid, kTailThreads);
+      GaussH H{S.taper_a, 1.0f / (float)(1 << log2M)};
+      filter_pairs(z, log2M, plan, tw, H, tid, kTailThreads);
+      fft_inverse(z, log2M, plan, tw, tid, kTailThreads);
+      // ---------------- onto the observed pixels, continuum, chi2
+      const double pmax = (double)(N2 - 1);
+      for (int j = tid; j < P.n_obs; j += kTailThreads) {
+        const double pp = (__ldg(P.obs_lnw + j) - S.u0) * S.inv_du;
+        double m;
+        if (!(pp >= 0.0 && pp <= pmax)) m = nan;            // smoothing.py:289 left/right = nan
+        else {
+          const int k = min((int)pp, N2 - 2);
+          const float dl = (float)(pp - (double)k);
+          const float t = dl * (1.f + (dl - 1.f) * S.hdu);   // (e^{dl du}-1)/(e^{du}-1) to O(du^2)
+          const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
+          m = 1.0 + (double)(g0 + t * (g1 - g0));
+        }
+        if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
+        if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
+        const double r = m * (double)__ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
+        acc += r * r;
+      }
+    } else {
+      // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289)
+      const int n = P.n;
+      const double wlo = __ldg(P.w) * S.D, whi = __ldg(P.w + n - 1) * S.D;
+      for (int j = tid; j < P.n_obs; j += kTailThreads) {
+        const double x = __ldg(P.obs_w + j);
+        double m;
+        if (!(x >= wlo && x <= whi)) m = nan;
+        else {
+          const int g = (int)((__ldg(P.obs_lnw + j) - S.lnD - P.lnw0) * P.inv_dlnw);
+          const int jj = locate(P.w, S.D, x, g, 0, n - 2);
+          const double wa = __ldg(P.w + jj) * S.D, wb = __ldg(P.w + jj + 1) * S.D;
+          const double a = (double)depth_of(row[jj], is_depth, false);
+          const double b = (double)depth_of(row[jj + 1], is_depth, false);
+          m = 1.0 + ((b - a) / (wb - wa) * (x - wa) + a);
+        }
+        if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
+        if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
+        const double r = m * (double)__ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
+        acc += r * r;
+      }
+    }
+    // ---------------- block reduction -> one lnL per live point (likelihood.py:117)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0 && P.lnl) {
+      double c2 = 0.0;
+#pragma unroll
+      for (int wdx = 0; wdx < kTailThreads / 32; ++wdx) c2 += red[wdx];
+      if (P.chi2_sed) c2 += P.chi2_sed[p];
+      P.lnl[p] = -0.5 * c2;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace payne
