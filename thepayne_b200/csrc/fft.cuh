@@ -43,6 +43,35 @@ __device__ __forceinline__ float2 rotcs(float2 a, float c, float s) {
              : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
 }
 
+// Same with the constant given as hi + lo floats.  Rounded to a single float, 1/sqrt(2),
+// cos(pi/8) and sin(pi/8) are all 1.6e-8 .. 3.1e-8 LOW, and they sit on fixed paths of every
+// pass: a coherent amplitude loss of the whole transform pair that shows up in lnL (an error
+// correlated with the residual), unlike the zero-mean rounding of everything else.
+template <bool INV>
+__device__ __forceinline__ float2 rotcs2(float2 a, float ch, float cl, float sh, float sl) {
+  if (INV)
+    return make_float2(fmaf(a.x, ch, -(a.y * sh)) + fmaf(a.x, cl, -(a.y * sl)),
+                       fmaf(a.y, ch, a.x * sh) + fmaf(a.y, cl, a.x * sl));
+  return make_float2(fmaf(a.x, ch, a.y * sh) + fmaf(a.x, cl, a.y * sl),
+                     fmaf(a.y, ch, -(a.x * sh)) + fmaf(a.y, cl, -(a.x * sl)));
+}
+constexpr float kRh = 0.7071067690849304f, kRl = 1.2101617485882343e-08f;     // 1/sqrt(2)
+constexpr float kC1h = 0.9238795042037964f, kC1l = 2.830748968563057e-08f;    // cos(pi/8)
+constexpr float kS1h = 0.3826834261417389f, kS1l = 6.2233507236442165e-09f;   // sin(pi/8)
+// multiply by exp(-/+ i pi/4) and exp(-/+ 3 i pi/4): (x +- y) / sqrt(2) patterns
+template <bool INV>
+__device__ __forceinline__ float2 rot45(float2 a) {
+  const float p = a.x + a.y, m = a.y - a.x;       // fwd: (x+y, y-x) r ; inv: (x-y, x+y) r
+  if (INV) return make_float2(fmaf(-m, kRl, -m * kRh), fmaf(p, kRl, p * kRh));
+  return make_float2(fmaf(p, kRl, p * kRh), fmaf(m, kRl, m * kRh));
+}
+template <bool INV>
+__device__ __forceinline__ float2 rot135(float2 a) {
+  const float p = a.x + a.y, m = a.y - a.x;       // fwd: (y-x, -(x+y)) r ; inv: (-(x+y), x-y) r
+  if (INV) return make_float2(fmaf(-p, kRl, -p * kRh), fmaf(-m, kRl, -m * kRh));
+  return make_float2(fmaf(m, kRl, m * kRh), fmaf(-p, kRl, -p * kRh));
+}
+
 template <bool INV>
 __device__ __forceinline__ void dft2(float2 (&v)[2]) {
   float2 t = v[0];
@@ -56,13 +85,12 @@ __device__ __forceinline__ void dft4(float2 (&v)[4]) {
 }
 template <bool INV>
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
-  constexpr float r = 0.70710678118654752440f;
   float2 b[4], c[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) { b[m] = v[m] + v[m + 4]; c[m] = v[m] - v[m + 4]; }
-  c[1] = rotcs<INV>(c[1], r, r);
+  c[1] = rot45<INV>(c[1]);
   c[2] = rot90<INV>(c[2]);
-  c[3] = rotcs<INV>(c[3], -r, r);
+  c[3] = rot135<INV>(c[3]);
   dft4<INV>(b);
   dft4<INV>(c);
 #pragma unroll
@@ -70,18 +98,16 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 }
 template <bool INV>
 __device__ __forceinline__ void dft16(float2 (&v)[16]) {
-  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
-  constexpr float r = 0.70710678118654752440f;
   float2 b[8], c[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) { b[m] = v[m] + v[m + 8]; c[m] = v[m] - v[m + 8]; }
-  c[1] = rotcs<INV>(c[1], c1, s1);
-  c[2] = rotcs<INV>(c[2], r, r);
-  c[3] = rotcs<INV>(c[3], s1, c1);
+  c[1] = rotcs2<INV>(c[1], kC1h, kC1l, kS1h, kS1l);
+  c[2] = rot45<INV>(c[2]);
+  c[3] = rotcs2<INV>(c[3], kS1h, kS1l, kC1h, kC1l);
   c[4] = rot90<INV>(c[4]);
-  c[5] = rotcs<INV>(c[5], -s1, c1);
-  c[6] = rotcs<INV>(c[6], -r, r);
-  c[7] = rotcs<INV>(c[7], -c1, s1);
+  c[5] = rotcs2<INV>(c[5], -kS1h, -kS1l, kC1h, kC1l);
+  c[6] = rot135<INV>(c[6]);
+  c[7] = rotcs2<INV>(c[7], -kC1h, -kC1l, kS1h, kS1l);
   dft8<INV>(b);
   dft8<INV>(c);
 #pragma unroll

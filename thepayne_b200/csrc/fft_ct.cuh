@@ -1,0 +1,206 @@
+// Compile-time-planned variant of the in-shared-memory FFT convolution of fft.cuh (same
+// algorithm, same storage swizzle, same digit-reversed filter stage) for the fast tail.
+//
+// What changes relative to fft.cuh:
+//  * the radix plan is constexpr, so every shift/stride is an immediate and the digit reversal
+//    of the filter stage unrolls to a few bit-field moves (no local-memory plan array);
+//  * twiddles are hoisted: a thread's butterflies in one pass share j = tid mod S, so the R-1
+//    factors W_L^{jq} are loaded ONCE per pass (a 22 KB, L1-resident subset of the table); in
+//    the first pass of a large transform (S > blockDim) the i-th butterfly needs
+//    W_L^{(tid + NT i) q} = W_L^{tid q} * exp(-2 pi i NT i q / L): base factor times a constant
+//    that lives in the kernel-parameter (constant) bank.
+#pragma once
+#include "fft.cuh"
+
+namespace payne {
+
+constexpr int kNT = 256;   // threads per CTA in the tail kernels
+
+template <int LOG2M>
+struct CtPlan {
+  // log2 radices of the strided passes; the contiguous radix-16 pass follows.
+  static constexpr int rest0 = LOG2M - 4;
+  __host__ __device__ static constexpr int pick(int rest) {
+    return (rest == 5 || rest % 3 == 0) ? 3 : (rest >= 4 ? 4 : rest);
+  }
+  static constexpr int r0 = rest0 > 0 ? pick(rest0) : 0;
+  static constexpr int rest1 = rest0 - r0;
+  static constexpr int r1 = rest1 > 0 ? pick(rest1) : 0;
+  static constexpr int rest2 = rest1 - r1;
+  static constexpr int r2 = rest2 > 0 ? pick(rest2) : 0;
+  static constexpr int rest3 = rest2 - r2;
+  static constexpr int r3 = rest3 > 0 ? pick(rest3) : 0;
+  static_assert(rest3 - r3 == 0, "plan needs more than four strided passes");
+  static constexpr int n = (r0 > 0) + (r1 > 0) + (r2 > 0) + (r3 > 0);
+  __host__ __device__ static constexpr int lr(int i) { return i == 0 ? r0 : i == 1 ? r1 : i == 2 ? r2 : r3; }
+  __host__ __device__ static constexpr int log2L(int i) {   // sub-transform length entering pass i
+    return i == 0 ? LOG2M : i == 1 ? LOG2M - r0 : i == 2 ? LOG2M - r0 - r1 : LOG2M - r0 - r1 - r2;
+  }
+  __device__ static __forceinline__ int row_of(int klo) {
+    int row = 0;
+    int l = LOG2M - 4;
+    if (r0 > 0) { l -= r0; row += (klo & ((1 << r0) - 1)) << l; klo >>= r0; }
+    if (r1 > 0) { l -= r1; row += (klo & ((1 << r1) - 1)) << l; klo >>= r1; }
+    if (r2 > 0) { l -= r2; row += (klo & ((1 << r2) - 1)) << l; klo >>= r2; }
+    if (r3 > 0) { l -= r3; row += (klo & ((1 << r3) - 1)) << l; }
+    return row;
+  }
+};
+
+// First-pass constants exp(-2 pi i * ip * kNT * q / M) for transforms with M/R > kNT.
+struct TwConst {
+  float2 c[2][4][16];   // [log2M - 13][ip][q]
+};
+
+struct TwTab {
+  const float2* __restrict__ tab;   // exp(-2 pi i e / 2^log2n), e < 2^(log2n-1)
+  int log2n;
+};
+
+template <int LOG2L>
+__device__ __forceinline__ float2 tw_load(const TwTab& tw, int x) {   // W_L^x, 0 <= x < L
+  const int sh = tw.log2n - LOG2L;
+  const int e = x << sh;
+  const int half = 1 << (tw.log2n - 1);
+  float2 w = __ldg(tw.tab + (e & (half - 1)));
+  if (e & half) { w.x = -w.x; w.y = -w.y; }
+  return w;
+}
+
+template <int LOG2M, int PASS, bool INV>
+__device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  using P = CtPlan<LOG2M>;
+  constexpr int LR = P::lr(PASS), R = 1 << LR, LOG2L = P::log2L(PASS), LOG2S = LOG2L - LR, S = 1 << LOG2S;
+  constexpr int NBF = (1 << (LOG2M - LR));             // butterflies in the pass
+  constexpr int NB = (NBF + kNT - 1) / kNT;            // per thread
+  constexpr int SPAN = S > kNT ? S / kNT : 1;          // distinct j per thread
+  static_assert(SPAN <= 4, "first pass too wide for the constant table");
+  static_assert(SPAN == 1 || (PASS == 0 && LOG2M >= 13 && LOG2M <= 14), "constant table covers log2M 13..14");
+  const int jb = tid & (S - 1);
+  float2 wb[R];
+#pragma unroll
+  for (int q = 1; q < R; ++q) wb[q] = tw_load<LOG2L>(tw, jb * q);
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int g = tid + kNT * i;
+    if (NBF % kNT != 0 && g >= NBF) break;
+    const int b = g >> LOG2S, j = g & (S - 1);
+    const int base = (b << LOG2L) + j;
+    float2 v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = z[swz(base + (m << LOG2S))];
+    constexpr int kSet = LOG2M >= 13 ? LOG2M - 13 : 0;
+    const int ip = i % SPAN;
+    if constexpr (!INV) {
+      dftR<R, false>(v);
+#pragma unroll
+      for (int q = 1; q < R; ++q) {
+        float2 w = wb[q];
+        if (SPAN > 1 && ip != 0) w = cmul(w, tc.c[kSet][ip][q]);
+        v[q] = cmul(v[q], w);
+      }
+    } else {
+#pragma unroll
+      for (int q = 1; q < R; ++q) {
+        float2 w = wb[q];
+        if (SPAN > 1 && ip != 0) w = cmul(w, tc.c[kSet][ip][q]);
+        v[q] = cmulc(v[q], w);
+      }
+      dftR<R, true>(v);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) z[swz(base + (m << LOG2S))] = v[m];
+  }
+}
+
+template <int LOG2M, bool INV>
+__device__ __forceinline__ void ct_contiguous16(float2* z, int tid) {
+  float4* z4 = reinterpret_cast<float4*>(z);
+  constexpr int NG = 1 << (LOG2M - 4);
+#pragma unroll
+  for (int i = 0; i < (NG + kNT - 1) / kNT; ++i) {
+    const int g = tid + kNT * i;
+    if (NG % kNT != 0 && g >= NG) break;
+    float4* p = z4 + 8 * g;
+    const int x = g & 7;
+    float2 v[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 u = p[c ^ x];
+      v[2 * c] = make_float2(u.x, u.y);
+      v[2 * c + 1] = make_float2(u.z, u.w);
+    }
+    dft16<INV>(v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) p[c ^ x] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+  }
+}
+
+template <int LOG2M>
+__device__ __forceinline__ void ct_fft_forward(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  using P = CtPlan<LOG2M>;
+  if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, false>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, false>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, false>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, false>(z, tw, tc, tid); __syncthreads(); }
+  ct_contiguous16<LOG2M, false>(z, tid);
+  __syncthreads();
+}
+template <int LOG2M>
+__device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  using P = CtPlan<LOG2M>;
+  ct_contiguous16<LOG2M, true>(z, tid);
+  __syncthreads();
+  if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, true>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, true>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, true>(z, tw, tc, tid); __syncthreads(); }
+  if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, true>(z, tw, tc, tid); __syncthreads(); }
+}
+
+// Filter stage on digit-reversed storage; H(k), k in [0, M], includes the 1/M of the inverse.
+// Work item w = tid + kNT i  ->  (klo = w >> 4, c = w & 15): c is fixed per thread, so the factor
+// exp(-2 pi i c / 32) of the untangling twiddle W_N^k, k = klo + c M/16, is a per-thread constant.
+template <int LOG2M, class HF>
+__device__ __forceinline__ void ct_filter_pairs(float2* z, const TwTab& tw, const HF& H, int tid) {
+  using P = CtPlan<LOG2M>;
+  constexpr int M = 1 << LOG2M, Mlo = M >> 4;
+  constexpr int NITEMS = ((Mlo >> 1) + 1) << 4;
+  const int c = tid & 15;
+  const float2 wc = tw_load<5>(tw, c);                  // exp(-2 pi i c / 32)
+#pragma unroll 2
+  for (int w = tid; w < NITEMS; w += kNT) {
+    const int klo = w >> 4;
+    int klo_p, c_p;
+    if (klo == 0) {
+      if (c > 8) continue;
+      klo_p = 0; c_p = (16 - c) & 15;
+    } else {
+      klo_p = Mlo - klo; c_p = 15 - c;
+      if (klo_p == klo && c > 7) continue;
+    }
+    const int k = klo + (c << (LOG2M - 4));
+    const int pk = swz((P::row_of(klo) << 4) + c);
+    const int pp = swz((P::row_of(klo_p) << 4) + c_p);
+    const float2 Zk = z[pk], Zp = z[pp];
+    const float2 W = cmul(tw_load<LOG2M + 1>(tw, klo), wc);   // exp(-2 pi i k / N)
+    const float hk = H(k), hm = H(M - k);
+    const float A = 0.5f * (hk + hm), Bc = 0.5f * (hk - hm);
+    const float2 E = make_float2(0.5f * (Zk.x + Zp.x), 0.5f * (Zk.y - Zp.y));
+    const float2 O = make_float2(0.5f * (Zk.y + Zp.y), -0.5f * (Zk.x - Zp.x));
+    const float2 WO = cmul(W, O), WcE = cmulc(E, W);
+    const float2 E2 = make_float2(A * E.x + Bc * WO.x, A * E.y + Bc * WO.y);
+    const float2 O2 = make_float2(Bc * WcE.x + A * O.x, Bc * WcE.y + A * O.y);
+    z[pk] = make_float2(E2.x - O2.y, E2.y + O2.x);
+    if (pp != pk) z[pp] = make_float2(E2.x + O2.y, O2.x - E2.y);
+  }
+  __syncthreads();
+}
+
+template <int LOG2M, class HF>
+__device__ __forceinline__ void ct_convolve(float2* z, const TwTab& tw, const TwConst& tc, const HF& H, int tid) {
+  ct_fft_forward<LOG2M>(z, tw, tc, tid);
+  ct_filter_pairs<LOG2M>(z, tw, H, tid);
+  ct_fft_inverse<LOG2M>(z, tw, tc, tid);
+}
+
+}  // namespace payne

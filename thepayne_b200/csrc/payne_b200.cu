@@ -17,6 +17,7 @@
 #include "mlp_tc.cuh"
 #include "phot.cuh"
 #include "tail.cuh"
+#include "tail_fast.cuh"
 
 namespace {
 
@@ -106,9 +107,12 @@ struct PayneCtx {
   payne::TcWeights tcw[6];
   payne::EncodeParams enc{};
   payne::TailParams tail{};
+  payne::FastGrid fast{};
   size_t tail_smem = 0;
-  int tail_grid = 0;
+  int tail_grid = 0, tail_grid_fast = 0;
   int grid_loguniform = 0;
+  int use_fast = 0;        // analytic-regrid tail selected (log-uniform emulator grid)
+  int allow_fast = 1;
   // photometry
   bool has_phot = false;
   payne::PhotParams phot{};
@@ -266,6 +270,77 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   for (int i = 0; i < PAYNE_MAX_POLY; ++i) T.poly_col[i] = c->lay.poly_col[i];
   c->ldf = ((long long)n + 3) / 4 * 4;
 
+  // ---- analytic regrid constants for the fast tail, verified against the exact tables
+  {
+    FastGrid& F = c->fast;
+    const double dlnw = (std::log(w[n - 1]) - std::log(w[0])) / (double)(n - 1);
+    F.dlnw = dlnw; F.inv_dlnw = 1.0 / dlnw;
+    F.f_num = n - 1; F.f_den = N1 - 1;
+    F.f_incj = (int)(((long long)kNT * F.f_num) / F.f_den);
+    F.f_incr = (int)(((long long)kNT * F.f_num) % F.f_den);
+    F.b_num = N1 - 1; F.b_den = n - 1;
+    F.b_incj = (int)(((long long)kNT * F.b_num) / F.b_den);
+    F.b_incr = (int)(((long long)kNT * F.b_num) % F.b_den);
+    F.f_invden = 1.0f / (float)F.f_den; F.b_invden = 1.0f / (float)F.b_den;
+    F.c_native = (float)(0.5 * dlnw);
+    F.c_grid1 = (float)(0.5 * dlnw * (double)(n - 1) / (double)(N1 - 1));
+    double worst = maxdev;
+    for (int k = 0; k < N1; ++k) {
+      const long long v = (long long)k * F.f_num;
+      int j = (int)(v / F.f_den); double dl = (double)(v % F.f_den) / (double)F.f_den;
+      if (j >= n - 1) { j = n - 2; dl = 1.0; }
+      const double ta = dl * (1.0 + (dl - 1.0) * (double)F.c_native);
+      float te; std::memcpy(&te, &fwd[k].y, 4);
+      worst = std::max(worst, std::fabs(((double)j + ta) - ((double)fwd[k].x + (double)te)));
+    }
+    for (int i = 1; i + 1 < n; ++i) {
+      const long long v = (long long)i * F.b_num;
+      int k = (int)(v / F.b_den); double dl = (double)(v % F.b_den) / (double)F.b_den;
+      if (k >= N1 - 1) { k = N1 - 2; dl = 1.0; }
+      const double ta = dl * (1.0 + (dl - 1.0) * (double)F.c_grid1);
+      float te; std::memcpy(&te, &back[i].y, 4);
+      worst = std::max(worst, std::fabs(((double)k + ta) - ((double)back[i].x + (double)te)));
+    }
+    c->use_fast = (worst < 2e-7) && l2 >= 10 && l2 <= 15;
+    std::vector<double> oq(no);
+    std::vector<float> ois(no), oot(no);
+    for (int j = 0; j < no; ++j) {
+      oq[j] = (lnw[j] - T.lnw0) * F.inv_dlnw;
+      ois[j] = (float)(1.0 / obs->eflux[j]);
+      oot[j] = (float)((obs->flux[j] - 1.0) / obs->eflux[j]);
+    }
+    double* dq; float *dis, *dot;
+    rc = upload_owned(c, &dq, oq.data(), no); if (rc) return rc;
+    rc = upload_owned(c, &dis, ois.data(), no); if (rc) return rc;
+    rc = upload_owned(c, &dot, oot.data(), no); if (rc) return rc;
+    F.obs_q = dq; F.obs_inv_s_f = dis; F.obs_ot_f = dot;
+    for (int set = 0; set < 2; ++set)
+      for (int ip = 0; ip < 4; ++ip)
+        for (int q = 0; q < 16; ++q) {
+          const double M = (double)(1 << (13 + set));
+          const double a = -2.0 * 3.14159265358979323846 * (double)ip * (double)kNT * (double)q / M;
+          F.twc.c[set][ip][q] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+  }
+  if (c->use_fast) {
+    int occf = 0;
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+#define PAYNE_FAST_CASE(L)                                                                           \
+    case L:                                                                                          \
+      e1 = cudaFuncSetAttribute(payne::tail_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)c->tail_smem);                                                  \
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, payne::tail_fast_kernel<L>, payne::kNT, \
+                                                         c->tail_smem);                              \
+      break;
+    switch (l2) {
+      PAYNE_FAST_CASE(10) PAYNE_FAST_CASE(11) PAYNE_FAST_CASE(12) PAYNE_FAST_CASE(13)
+      PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15)
+      default: break;
+    }
+#undef PAYNE_FAST_CASE
+    if (e1 != cudaSuccess || e2 != cudaSuccess || occf < 1) c->use_fast = 0;
+    c->tail_grid_fast = occf * c->sm_count;
+  }
   CU_TRY(cudaFuncSetAttribute(payne::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->tail_smem));
   int occ = 0;
@@ -407,7 +482,19 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       T.lnl = lnl ? lnl + p0 : nullptr;
       T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
       T.status = c->status;
-      tail_kernel<<<std::min(c->tail_grid, nb), kTailThreads, c->tail_smem, st>>>(T);
+      if (c->use_fast && c->allow_fast) {
+        const int grid = std::min(c->tail_grid_fast, nb);
+        switch (T.log2N1) {
+          case 10: tail_fast_kernel<10><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 11: tail_fast_kernel<11><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 12: tail_fast_kernel<12><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 13: tail_fast_kernel<13><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 14: tail_fast_kernel<14><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          default: tail_fast_kernel<15><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+        }
+      } else {
+        tail_kernel<<<std::min(c->tail_grid, nb), kTailThreads, c->tail_smem, st>>>(T);
+      }
       c->launches++;
     } else if (lnl) {
       lnl_from_sed_kernel<<<(nb + 255) / 256, 256, 0, st>>>(c->chi2_sed, lnl + p0, nb);
@@ -538,6 +625,7 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "nfft1") return c->has_spec ? (1LL << c->tail.log2N1) : 0;
   if (k == "launches") return c->launches;
   if (k == "grid_loguniform") return c->grid_loguniform;
+  if (k == "fast_tail") return c->use_fast && c->allow_fast;
   if (k == "max_batch") return c->slab;
   if (k == "sm_count") return c->sm_count;
   if (k == "tail_grid") return c->tail_grid;
@@ -566,6 +654,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
     return PAYNE_OK;
   }
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
+  if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
   return fail(PAYNE_E_INVALID, "unknown key " + k);
 }
 

@@ -1,0 +1,239 @@
+// Fast fused tail for emulators trained on a log-uniform wavelength grid (the grid every
+// Payne trainer produces: Payne/utils/readc3k.py:441-451).  Same semantics as tail.cuh (which
+// stays as the general-grid path); what differs is HOW the four np.interp regrids are done:
+//
+// On a log-uniform grid  w_i = w_0 q^i  every regrid of Payne/utils/smoothing.py:649-668 maps
+// index k of one uniform-in-ln(lambda) grid to position  p = k * num / den  of another, an exact
+// rational.  The bracketing index is floor(p) and the np.interp weight is
+//     t = (e^{delta a} - 1) / (e^{a} - 1) = delta (1 + (delta - 1) a/2 + O(a^2)),
+// delta = frac(p), a = the (tiny, ~3e-6) log-spacing of the source grid.  So the per-dataset
+// tables and the per-point fp64 searches of the general path collapse into incremental integer
+// arithmetic: each thread walks k -> k + 256 with (j, rem) += (inc_j, inc_rem).  The host
+// verifies at context creation that these analytic weights reproduce the exact np.interp tables
+// to < 2e-7 before this kernel is selected.
+#pragma once
+#include "fft_ct.cuh"
+#include "tail.cuh"
+
+namespace payne {
+
+struct FastGrid {
+  // stage 1 forward (native -> 2^k grid) and back: p = k * num / den
+  int f_num, f_den, f_incj, f_incr;   // num = n-1,  den = N1-1, inc = divmod(256*num, den)
+  int b_num, b_den, b_incj, b_incr;   // num = N1-1, den = n-1
+  float f_invden, b_invden;
+  float c_native;                     // dlnw / 2   (source spacing = native grid)
+  float c_grid1;                      // du1 / 2    (source spacing = stage-1 grid)
+  double dlnw, inv_dlnw;
+  const double* obs_q;                // [n_obs] (ln lambda_j - ln w_0) / dlnw
+  const float* obs_inv_s_f;           // [n_obs] 1/eflux
+  const float* obs_ot_f;              // [n_obs] (flux - 1)/eflux
+  TwConst twc;
+};
+
+struct FastSetup {
+  int s_incj, s_incr, s_den, s_num;   // stage 2: num = nM-1, den = N2-1
+  float s_invden;
+  double q0, scale;                   // final: p = (obs_q - q0) * scale
+};
+
+template <class T>
+__device__ __forceinline__ void divmod_init(int tid, int num, int den, int& j, int& rem) {
+  const long long v = (long long)tid * num;
+  j = (int)(v / den);
+  rem = (int)(v - (long long)j * den);
+}
+
+__device__ __forceinline__ float interp_w(float delta, float c) {   // delta (1 + (delta-1) c)
+  return fmaf(delta * (delta - 1.f), c, delta);
+}
+
+template <int LOG2N1>
+__global__ void __launch_bounds__(kNT, LOG2N1 <= 14 ? 3 : 1)
+tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float* zf = reinterpret_cast<float*>(smem_raw);
+  __shared__ PointSetup S;
+  __shared__ FastSetup FS;
+  __shared__ double red[kNT / 32];
+  const int tid = threadIdx.x;
+  const TwTab tw{P.tw, P.log2tw};
+  const double nan = CUDART_NAN;
+  constexpr int N1 = 1 << LOG2N1;
+
+  for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
+    const double* th = P.theta + (long long)p * P.ld;
+    float* row = P.flux + (long long)p * P.ldf;
+    if (tid == 0) {
+      tail_setup(P, th, S);
+      if (!S.bad && S.use_inst) {
+        const int nM = S.i1 - S.i0 + 1, N2 = 1 << S.log2N2;
+        FS.s_num = nM - 1; FS.s_den = N2 - 1;
+        const long long inc = (long long)kNT * (nM - 1);
+        FS.s_incj = (int)(inc / (N2 - 1));
+        FS.s_incr = (int)(inc - (long long)FS.s_incj * (N2 - 1));
+        FS.s_invden = 1.0f / (float)(N2 - 1);
+        FS.scale = (double)(N2 - 1) / (double)(nM - 1);
+        FS.q0 = (double)S.i0 + S.lnD * F.inv_dlnw;
+      }
+    }
+    __syncthreads();
+    if (S.bad) {
+      if (P.model_out)
+        for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
+      if (tid == 0 && P.lnl) P.lnl[p] = nan;
+      __syncthreads();
+      continue;
+    }
+    bool is_depth = false;
+
+    // ---------------- stage 1: rotational broadening on the full emulator grid
+    if (S.do_rot) {
+      const int n = P.n;
+      {
+        int j, rem;
+        divmod_init<int>(tid, F.f_num, F.f_den, j, rem);
+#pragma unroll 4
+        for (int k = tid; k < N1; k += kNT) {
+          int jj = j; float dl = (float)rem * F.f_invden;
+          if (jj >= n - 1) { jj = n - 2; dl = 1.f; }
+          const float a = depth_of(row[jj], false, true), b = depth_of(row[jj + 1], false, true);
+          zf[zidx(k)] = fmaf(interp_w(dl, F.c_native), b - a, a);
+          j += F.f_incj; rem += F.f_incr;
+          if (rem >= F.f_den) { rem -= F.f_den; ++j; }
+        }
+      }
+      __syncthreads();
+      RotH H{P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
+      ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
+      {
+        int k, rem;
+        divmod_init<int>(tid, F.b_num, F.b_den, k, rem);
+#pragma unroll 4
+        for (int i = tid; i < n; i += kNT) {
+          int kk = k; float dl = (float)rem * F.b_invden;
+          if (kk >= N1 - 1) { kk = N1 - 2; dl = 1.f; }
+          const float g0 = zf[zidx(kk)], g1 = zf[zidx(kk + 1)];
+          const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
+          if (i > 0 && i < n - 1) {                  // edge patch of predictspec.py:240-241
+            row[i] = v;
+            if (i == 1) row[0] = v;
+            if (i == n - 2) row[n - 1] = v;
+          }
+          k += F.b_incj; rem += F.b_incr;
+          if (rem >= F.b_den) { rem -= F.b_den; ++k; }
+        }
+      }
+      is_depth = true;
+      __syncthreads();
+    }
+
+    double acc = 0.0;
+    if (S.use_inst) {
+      // ---------------- stage 2: mask, regrid, Gaussian broadening
+      const int log2N2 = S.log2N2, N2 = 1 << log2N2;
+      const int i0 = S.i0, i1 = S.i1;
+      {
+        int j, rem;
+        divmod_init<int>(tid, FS.s_num, FS.s_den, j, rem);
+        j += i0;
+        const int incj = FS.s_incj, incr = FS.s_incr, den = FS.s_den;
+        const float invden = FS.s_invden;
+#pragma unroll 4
+        for (int k = tid; k < N2; k += kNT) {
+          int jj = j; float dl = (float)rem * invden;
+          if (jj >= i1) { jj = i1 - 1; dl = 1.f; }
+          const float a = depth_of(row[jj], is_depth, true), b = depth_of(row[jj + 1], is_depth, true);
+          zf[zidx(k)] = fmaf(interp_w(dl, F.c_native), b - a, a);
+          j += incj; rem += incr;
+          if (rem >= den) { rem -= den; ++j; }
+        }
+      }
+      __syncthreads();
+      GaussH H{S.taper_a, 2.0f / (float)N2};
+      if (log2N2 == LOG2N1) {
+        ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
+      } else if (LOG2N1 >= 10 && log2N2 == LOG2N1 - 1) {
+        ct_convolve<(LOG2N1 >= 10 ? LOG2N1 - 2 : 8)>(z, tw, F.twc, H, tid);
+      } else {
+        const Twiddles twr{P.tw, P.log2tw};
+        FftPlan plan; plan.make(log2N2 - 1);
+        fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
+        filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
+        fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
+      }
+      // ---------------- onto the observed pixels, continuum, chi2
+      const double pmax = (double)(N2 - 1);
+      const float hdu = S.hdu;
+      const double q0 = FS.q0, scale = FS.scale;
+      if (P.n_poly == 0 && P.model_out == nullptr) {
+#pragma unroll 4
+        for (int j = tid; j < P.n_obs; j += kNT) {
+          const double pp = (__ldg(F.obs_q + j) - q0) * scale;
+          float r;
+          if (!(pp >= 0.0 && pp <= pmax)) r = CUDART_NAN_F;        // smoothing.py:289 left/right = nan
+          else {
+            const int k = min((int)pp, N2 - 2);
+            const float dl = (float)(pp - (double)k);
+            const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
+            const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
+            r = fmaf(d, __ldg(F.obs_inv_s_f + j), -__ldg(F.obs_ot_f + j));
+          }
+          acc = fma((double)r, (double)r, acc);
+        }
+      } else {
+        for (int j = tid; j < P.n_obs; j += kNT) {
+          const double pp = (__ldg(F.obs_q + j) - q0) * scale;
+          double m;
+          if (!(pp >= 0.0 && pp <= pmax)) m = nan;
+          else {
+            const int k = min((int)pp, N2 - 2);
+            const float dl = (float)(pp - (double)k);
+            const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
+            m = 1.0 + (double)fmaf(interp_w(dl, hdu), g1 - g0, g0);
+          }
+          if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
+          if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
+          const double r = m * __ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
+          acc += r * r;
+        }
+      }
+    } else {
+      // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289)
+      const int n = P.n;
+      const double wlo = __ldg(P.w) * S.D, whi = __ldg(P.w + n - 1) * S.D;
+      for (int j = tid; j < P.n_obs; j += kNT) {
+        const double x = __ldg(P.obs_w + j);
+        double m;
+        if (!(x >= wlo && x <= whi)) m = nan;
+        else {
+          const int g = (int)((__ldg(P.obs_lnw + j) - S.lnD - P.lnw0) * P.inv_dlnw);
+          const int jj = locate(P.w, S.D, x, g, 0, n - 2);
+          const double wa = __ldg(P.w + jj) * S.D, wb = __ldg(P.w + jj + 1) * S.D;
+          const double a = (double)depth_of(row[jj], is_depth, false);
+          const double b = (double)depth_of(row[jj + 1], is_depth, false);
+          m = 1.0 + ((b - a) / (wb - wa) * (x - wa) + a);
+        }
+        if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
+        if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
+        const double r = m * __ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
+        acc += r * r;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0 && P.lnl) {
+      double c2 = 0.0;
+#pragma unroll
+      for (int wdx = 0; wdx < kNT / 32; ++wdx) c2 += red[wdx];
+      if (P.chi2_sed) c2 += P.chi2_sed[p];
+      P.lnl[p] = -0.5 * c2;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace payne

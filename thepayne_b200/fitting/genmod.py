@@ -1,0 +1,51 @@
+"""Model generation with the reference's ``GenMod`` interface (Payne/fitting/genmod.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ..predict.predictsed import FastPayneSEDPredict
+from ..predict.predictspec import PayneSpecPredict
+
+
+class GenMod(object):
+    def __init__(self, *arg, **kwargs):
+        self.verbose = kwargs.get('verbose', False)
+        self.precision = kwargs.get('precision', 'parity')
+
+    def _initspecnn(self, nnpath=None, **kwargs):          # genmod.py:15-32
+        NNtype = kwargs.get('NNtype', 'LinNet')
+        self.PP = PayneSpecPredict(nnpath=nnpath, NNtype=NNtype, precision=self.precision)
+
+    def _initphotnn(self, filterarray, nnpath=None):       # genmod.py:35-43
+        self.filterarray = None if filterarray is None else list(filterarray)
+        self.fppsed = FastPayneSEDPredict(usebands=self.filterarray, nnpath=nnpath, precision=self.precision)
+        if self.filterarray is None:
+            self.filterarray = self.fppsed.filternames
+
+    def genspec(self, pars, outwave=None, verbose=False, modpoly=False, carbon_bool=False):
+        """genmod.py:58-108: pars = [Teff, logg, FeH, aFe, Vrad, Vrot, Vmic, Inst_R, pc_0...]."""
+        if carbon_bool:
+            raise NotImplementedError('carbon_bool is hard-wired off in the reference (fitstar.py:150-154)')
+        pars = [float(p) for p in pars]
+        polycoef = pars[8:] if modpoly else []
+        eng = self.PP.anns.engine_for(outwave, npoly=len(polycoef))
+        row = np.array([pars[:8] + list(polycoef)], dtype=np.float64)
+        flux, _, _ = eng.model_batch(row, want_mags=False)
+        wave = self.PP.anns.wavelength if outwave is None else outwave
+        return wave, flux[0].cpu().numpy()
+
+    def genphot(self, pars, rvfree=False, verbose=False):   # genmod.py:110-155
+        if rvfree:
+            raise NotImplementedError('rvfree is never set by the likelihood (likelihood.py:103-106)')
+        teff, logg, feh, afe, logR, dist, av = [float(p) for p in pars[:7]]
+        logt = np.log10(teff)
+        logl = 2.0 * logR + 4.0 * (logt - np.log10(5770.0))
+        sed = self.fppsed.sed(logt=logt, logg=logg, feh=feh, afe=afe, logl=logl, dist=dist, av=av, rv=3.1)
+        return {ff: s for s, ff in zip(sed, self.filterarray)}
+
+    def genphot_scaled(self, pars, rvfree=False, verbose=False):   # genmod.py:157-187
+        if rvfree:
+            raise NotImplementedError('rvfree is never set by the likelihood (likelihood.py:103-106)')
+        teff, logg, feh, afe, logA, av = [float(p) for p in pars[:6]]
+        sed = self.fppsed.sed(logt=np.log10(teff), logg=logg, feh=feh, afe=afe, logA=logA, av=av, rv=3.1)
+        return {ff: s for s, ff in zip(sed, self.filterarray)}

@@ -1,0 +1,136 @@
+"""Spectrum emulator front end with the reference's class and method names.
+
+Mirror of ``Payne/predict/predictspec.py``: ``ANN`` (:29-74) and ``PayneSpecPredict`` (:77-298).
+The arithmetic runs in libpayne_b200.so (tcgen05 MLP + fused broadening tail); these classes
+only translate the reference's keyword conventions into rows of a parameter matrix.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import annio
+from ..engine import Engine
+from ..synth import SpecNet
+
+speedoflight = 299792.458
+_FULL = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R']
+_FWHM = 2.355   # the kernel applies genmod.py:83's factor itself
+
+
+def _as_specnet(nnpath):
+    if isinstance(nnpath, SpecNet):
+        return nnpath
+    if nnpath is None:
+        raise IOError('no spectrum ANN given (the reference default data/ANN/NN.h5 is not shipped)')
+    return annio.load_specnet(nnpath)
+
+
+class ANN(object):
+    """predictspec.py:29-74 -- holds the network and evaluates it, batch-aware."""
+
+    def __init__(self, nnpath=None, **kwargs):
+        self.verbose = kwargs.get('verbose', False)
+        self.nnpath = nnpath
+        self.NNtype = kwargs.get('NNtype', 'LinNet')
+        if self.NNtype != 'LinNet':
+            raise NotImplementedError('only the sigmoid LinNet is accelerated (NNtype=%r)' % self.NNtype)
+        self.model = _as_specnet(nnpath)
+        self.inlabels = list(self.model.inlabels)
+        self.xmin, self.xmax = self.model.xmin, self.model.xmax
+        self.wavelength = self.model.wavelength
+        self.resolution = np.array(self.model.resolution, dtype=float)
+        self.precision = kwargs.get('precision', 'parity')
+        self._engines = {}
+
+    def engine_for(self, outwave=None, npoly=0):
+        """Engine whose observed grid is ``outwave`` (None -> the emulator's own grid)."""
+        ow = self.wavelength if outwave is None else np.ascontiguousarray(outwave, dtype=np.float64)
+        key = (ow.tobytes(), npoly)
+        if key not in self._engines:
+            if len(self._engines) > 8:
+                self._engines.pop(next(iter(self._engines))).close()
+            one = np.ones(len(ow))
+            fit = _FULL + ['pc_%d' % k for k in range(npoly)]
+            self._engines[key] = Engine(spec=self.model, obs_wave=ow, obs_flux=one, obs_eflux=one,
+                                        fitpars_i=fit, runbools=(True, False, npoly > 0, False, False),
+                                        precision=self.precision)
+        return self._engines[key]
+
+    def eval(self, x):
+        """labels [D_in] or [B, D_in] -> flux [D_out] or [B, D_out] float32 (predictspec.py:61-74)."""
+        if isinstance(x, list):
+            x = np.asarray(x)
+        x = np.asarray(x, dtype=np.float64)
+        y = self.engine_for().ann_eval(x.reshape(-1, self.model.D_in))
+        return y.cpu().numpy().squeeze()
+
+
+class PayneSpecPredict(object):
+    """predictspec.py:77-298."""
+
+    def __init__(self, nnpath=None, **kwargs):
+        self.NN = {}
+        self.nnpath = nnpath
+        self.NNtype = kwargs.get('NNtype', 'LinNet')
+        self.Cnnpath = kwargs.get('Cnnpath', None)
+        if self.Cnnpath is not None:
+            raise NotImplementedError('continuum ANN (Cnnpath) is outside the accelerated path')
+        self.anns = ANN(nnpath=nnpath, NNtype=self.NNtype, testing=False, verbose=False,
+                        precision=kwargs.get('precision', 'parity'))
+        self.Canns = None
+
+    def predictspec(self, labels):
+        return self.anns.eval(labels)
+
+    def _labels(self, kwargs):
+        """Keyword aliases of predictspec.py:154-198."""
+        d = {}
+        d['teff'] = kwargs['Teff'] if 'Teff' in kwargs else (10.0 ** kwargs['logt'] if 'logt' in kwargs else 5770.0)
+        d['logg'] = kwargs.get('log(g)', kwargs.get('logg', 4.44))
+        d['feh'] = kwargs.get('[Fe/H]', kwargs.get('feh', 0.0))
+        afe = 0.0
+        for k in ['[alpha/Fe]', '[a/Fe]', 'aFe', 'afe']:
+            if k in kwargs:
+                afe = kwargs[k]
+                break
+        d['afe'] = afe
+        vm = kwargs.get('vmic', np.nan)
+        d['vmic'] = vm if np.isfinite(vm) else np.nan
+        return d
+
+    def getspec(self, **kwargs):
+        """Model spectrum for one label set (predictspec.py:136-294); scalar ``inst_R`` only."""
+        self.inputdict = self._labels(kwargs)
+        outwave = kwargs.get('outwave', None)
+        rot = kwargs.get('rot_vel', 0.0)
+        rad = kwargs.get('rad_vel', 0.0)
+        inst = kwargs.get('inst_R', np.nan)
+        if not isinstance(inst, float):
+            raise NotImplementedError('LSF-vector inst_R is outside the accelerated path')
+        modwave = self.anns.wavelength
+        if outwave is None:
+            # no resampling of the wavelength axis: the reference returns the (shifted) native grid
+            grid = modwave * (1.0 + (rad / speedoflight)) if rad != 0.0 else modwave
+            eng = self.anns.engine_for(grid)
+        else:
+            outwave = np.array(outwave)
+            grid = outwave
+            eng = self.anns.engine_for(outwave)
+        d = self.inputdict
+        row = np.array([[d['teff'], d['logg'], d['feh'], d['afe'], rad, rot, d['vmic'],
+                         inst / _FWHM if inst > 0.0 else np.nan]], dtype=np.float64)
+        flux, _, _ = eng.model_batch(row, want_mags=False)
+        return grid, flux[0].cpu().numpy()
+
+    def getspec_batch(self, labels, rot_vel, rad_vel, inst_R, outwave, vmic=None):
+        """Batched extension: arrays of length B -> flux [B, len(outwave)] (CUDA tensor)."""
+        labels = np.asarray(labels, dtype=np.float64)
+        B = labels.shape[0]
+        th = np.full((B, 8), np.nan)
+        th[:, :4] = labels[:, :4]
+        th[:, 4], th[:, 5] = rad_vel, rot_vel
+        if vmic is not None:
+            th[:, 6] = vmic
+        th[:, 7] = np.asarray(inst_R, dtype=np.float64) / _FWHM
+        flux, _, _ = self.anns.engine_for(outwave).model_batch(th, want_mags=False)
+        return flux

@@ -71,10 +71,17 @@ def ann_wavegrid(w0: float, w1: float, r_fwhm: float):
     """Emulator pixel grid: ``w0*(1+1/(3 R_sigma))**i`` while <= w1
     (``readc3k.py:441-451``), with ``R_sigma = R_fwhm*2.35482``."""
     rsig = r_fwhm * SIGMA_TO_FWHM_TRAIN
-    n = int(np.floor(np.log(w1 / w0) / np.log1p(1.0 / (3.0 * rsig)))) + 2
-    i = np.arange(n, dtype=np.float64)
-    w = w0 * (1.0 + 1.0 / (3.0 * rsig)) ** i
-    w = w[w <= w1]
+    # scalar libm pow in a Python loop, exactly like the trainer: bit-reproducible across hosts
+    # (numpy's SIMD pow may differ in the last bit between CPU generations)
+    out, i = [], 1
+    while True:
+        wave_i = w0 * (1.0 + 1.0 / (3.0 * rsig)) ** (i - 1.0)
+        if wave_i <= w1:
+            out.append(wave_i)
+            i += 1
+        else:
+            break
+    w = np.array(out, dtype=np.float64)
     return w, rsig
 
 
