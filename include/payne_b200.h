@@ -59,15 +59,19 @@ enum {
 };
 #define PAYNE_MAX_POLY 16
 
-/* MLP arithmetic. PARITY reproduces the reference's fp32 Linear layers (error-compensated
- * 3xTF32 on the tensor cores, fp32 accumulate); the other two trade accuracy for speed and
- * do NOT meet the 1e-5 / 1e-3 parity bar (reported separately). SIMT_FP32 is a plain
- * CUDA-core fp32 FMA implementation kept as an on-device cross-check. */
+/* MLP arithmetic.  PARITY reproduces the reference's fp32 Linear layers on the tensor cores
+ * with an exact-accumulation split (three 8-bit fixed-point bf16 slices per operand, six bf16
+ * MMAs per product, fp32 accumulate in TMEM; see csrc/mlp_tc.cuh).  3XTF32 is the classic
+ * error-compensated TF32 split (kept for comparison: its accumulator truncation bias costs
+ * ~1e-2 in lnL).  TF32 trades accuracy for speed and does NOT meet the 1e-5 / 1e-3 parity bar
+ * (reported separately).  SIMT_FP32 is a plain CUDA-core fp32 FMA implementation kept as an
+ * on-device cross-check.  BF16 is reserved. */
 enum {
-  PAYNE_PREC_PARITY_3XTF32 = 0,
+  PAYNE_PREC_PARITY = 0,
   PAYNE_PREC_TF32 = 1,
   PAYNE_PREC_BF16 = 2,
-  PAYNE_PREC_SIMT_FP32 = 3
+  PAYNE_PREC_SIMT_FP32 = 3,
+  PAYNE_PREC_3XTF32 = 4
 };
 
 /* Spectrum emulator: LinNet (NNmodels.py:140-168); HOST pointers, copied at create.
@@ -144,6 +148,12 @@ int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, 
 int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
 /* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points). */
 int payne_ctx_set(PayneCtx* ctx, const char* key, int64_t value);
+
+/* Kernel unit-test hook: C[M,N] = A[M,K] . W[N,K]^T + bias[N] through the tensor-core GEMM of
+ * the given PAYNE_PREC_* mode, HOST buffers in and out (A must lie in [0,1) for PARITY, like
+ * the sigmoid activations it is built for).  Synchronous. */
+int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_host, int M, int N, int K,
+                    int precision, int device, float* C_host);
 
 /* Per-kernel device time of the most recent payne_lnlike_batch call on this context,
  * measured with CUDA events on the launching stream when timing is enabled

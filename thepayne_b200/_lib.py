@@ -17,11 +17,11 @@ PAR_INDEX = {
     'Teff': 0, 'log(g)': 1, '[Fe/H]': 2, '[a/Fe]': 3, 'Vrad': 4, 'Vrot': 5, 'Vmic': 6,
     'Inst_R': 7, 'log(R)': 8, 'Dist': 9, 'log(A)': 10, 'Av': 11, 'Rv': 12,
 }
-PREC = {'parity': 0, '3xtf32': 0, 'tf32': 1, 'bf16': 2, 'simt': 3, 'fp32': 3}
+PREC = {'parity': 0, 'x3': 0, 'tf32': 1, 'bf16': 2, 'simt': 3, 'fp32': 3, '3xtf32': 4}
 
 EXPORTS = ['payne_abi_version', 'payne_last_error', 'payne_ctx_create', 'payne_ctx_destroy',
            'payne_lnlike_batch', 'payne_lnlike_batch_host', 'payne_model_batch', 'payne_ann_eval',
-           'payne_ctx_query', 'payne_ctx_set', 'payne_ctx_last_ms']
+           'payne_ctx_query', 'payne_ctx_set', 'payne_ctx_last_ms', 'payne_gemm_test']
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)
@@ -89,6 +89,8 @@ def load():
     lib.payne_ctx_set.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.payne_ctx_last_ms.restype = C.c_double
     lib.payne_ctx_last_ms.argtypes = [vp, C.c_int]
+    lib.payne_gemm_test.restype = C.c_int
+    lib.payne_gemm_test.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     _lib = lib
     return lib
 

@@ -45,31 +45,35 @@ __device__ __forceinline__ float2 rotcs(float2 a, float c, float s) {
 
 // Same with the constant given as hi + lo floats.  Rounded to a single float, 1/sqrt(2),
 // cos(pi/8) and sin(pi/8) are all 1.6e-8 .. 3.1e-8 LOW, and they sit on fixed paths of every
-// pass: a coherent amplitude loss of the whole transform pair that shows up in lnL (an error
-// correlated with the residual), unlike the zero-mean rounding of everything else.
+// pass: a coherent amplitude loss (-4.3e-8 per forward+inverse pair, reproduced in float32
+// numpy) that shows up in lnL as an error correlated with the residual, unlike the zero-mean
+// rounding of everything else.
+// The correction term must enter BEFORE the single rounding: fma(x, hi, x*lo), never
+// fma(x, lo, round(x*hi)) -- a term below half an ulp added to an already rounded value is lost.
 template <bool INV>
 __device__ __forceinline__ float2 rotcs2(float2 a, float ch, float cl, float sh, float sl) {
-  if (INV)
-    return make_float2(fmaf(a.x, ch, -(a.y * sh)) + fmaf(a.x, cl, -(a.y * sl)),
-                       fmaf(a.y, ch, a.x * sh) + fmaf(a.y, cl, a.x * sl));
-  return make_float2(fmaf(a.x, ch, a.y * sh) + fmaf(a.x, cl, a.y * sl),
-                     fmaf(a.y, ch, -(a.x * sh)) + fmaf(a.y, cl, -(a.x * sl)));
+  if (INV)   // (x c - y s, y c + x s)
+    return make_float2(fmaf(a.x, ch, fmaf(-a.y, sh, fmaf(a.x, cl, -(a.y * sl)))),
+                       fmaf(a.y, ch, fmaf(a.x, sh, fmaf(a.y, cl, a.x * sl))));
+  return make_float2(fmaf(a.x, ch, fmaf(a.y, sh, fmaf(a.x, cl, a.y * sl))),
+                     fmaf(a.y, ch, fmaf(-a.x, sh, fmaf(a.y, cl, -(a.x * sl)))));
 }
 constexpr float kRh = 0.7071067690849304f, kRl = 1.2101617485882343e-08f;     // 1/sqrt(2)
 constexpr float kC1h = 0.9238795042037964f, kC1l = 2.830748968563057e-08f;    // cos(pi/8)
 constexpr float kS1h = 0.3826834261417389f, kS1l = 6.2233507236442165e-09f;   // sin(pi/8)
+__device__ __forceinline__ float mul_r(float x) { return fmaf(x, kRh, x * kRl); }   // x / sqrt(2)
 // multiply by exp(-/+ i pi/4) and exp(-/+ 3 i pi/4): (x +- y) / sqrt(2) patterns
 template <bool INV>
 __device__ __forceinline__ float2 rot45(float2 a) {
   const float p = a.x + a.y, m = a.y - a.x;       // fwd: (x+y, y-x) r ; inv: (x-y, x+y) r
-  if (INV) return make_float2(fmaf(-m, kRl, -m * kRh), fmaf(p, kRl, p * kRh));
-  return make_float2(fmaf(p, kRl, p * kRh), fmaf(m, kRl, m * kRh));
+  if (INV) return make_float2(mul_r(-m), mul_r(p));
+  return make_float2(mul_r(p), mul_r(m));
 }
 template <bool INV>
 __device__ __forceinline__ float2 rot135(float2 a) {
   const float p = a.x + a.y, m = a.y - a.x;       // fwd: (y-x, -(x+y)) r ; inv: (-(x+y), x-y) r
-  if (INV) return make_float2(fmaf(-p, kRl, -p * kRh), fmaf(-m, kRl, -m * kRh));
-  return make_float2(fmaf(m, kRl, m * kRh), fmaf(-p, kRl, -p * kRh));
+  if (INV) return make_float2(mul_r(-p), mul_r(-m));
+  return make_float2(mul_r(m), mul_r(-p));
 }
 
 template <bool INV>

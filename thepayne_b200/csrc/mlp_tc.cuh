@@ -2,24 +2,37 @@
 //
 //   reference: Payne/train/NNmodels.py:154-162  sigmoid(lin_k(h)) for k=2..5, lin6 linear.
 //
-// The reference runs fp32 Linear layers; the tensor cores have no fp32 MMA, so the parity
-// mode splits every operand x into two TF32 numbers  x = hi + lo  (hi = rna_tf32(x),
-// lo = rna_tf32(x - hi)) and accumulates  Ahi.Whi + Ahi.Wlo + Alo.Whi  in fp32 in TMEM
-// ("3xTF32"): the dropped lo.lo term is ~2^-22 relative, i.e. fp32 round-off.
-// PAYNE_PREC_TF32 issues only Ahi.Whi.
+// The reference runs fp32 Linear layers; the tensor cores have no fp32 MMA.  Three operand
+// modes share one kernel:
+//
+//  X3 (parity mode)  "exact-accumulation" split.  Every operand is cut into three 8-bit
+//      fixed-point slices stored as bf16: activations h in (0,1) as h = p1 + p2 + p3 with
+//      p_i = k_i 2^-8i, |k_i| <= 256; weights row-wise as w = s_n (q1 + q2 + q3), s_n a power of
+//      two >= max|w_n|, q_i = k_i 2^-(8i-1), |k_i| <= 128.  The dominant product sum
+//      sum_k p1 q1 is then an integer multiple of 2^-15 below 2^24 for K <= 512 -- EXACTLY
+//      representable in the fp32 TMEM accumulator, so the tensor core never rounds it -- and
+//      the five cross terms p1q2, p2q1, p1q3, p2q2, p3q1 (<= 2^-8 of the result) go to a second
+//      accumulator whose rounding is ~2^-32 of the result.  Six bf16 MMAs (K=16) cost the same
+//      tensor time as three TF32 MMAs (K=8) but give a correctly rounded fp32 dot product
+//      (3xTF32 measured here: coherent ~1e-6 bias from fp32 accumulator truncation over 96
+//      MMA steps, which shows up as |dlnL| ~ 1e-2).
+//  T3  3xTF32 error-compensated split (hi/lo), kept for comparison.
+//  T1  1xTF32, fast mode (not a parity mode).
 //
 // Kernel anatomy (one CTA per SM, persistent over 128 x BN output tiles, 256 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled K-major boxes of the hi/lo
-//               operand planes into an NSTAGE ring, mbarrier complete_tx
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
-//               from shared-memory descriptors, tcgen05.commit frees the ring slot
-//   warp 2      TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns -> +bias (-> sigmoid -> hi/lo split)
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled K-major boxes of the operand
+//               planes into an NSTAGE ring, mbarrier complete_tx
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN) from shared-memory
+//               descriptors; tcgen05.commit frees the ring slot / publishes the accumulator
+//   warp 2      TMEM allocator (double-buffered accumulators)
+//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale, +bias (-> sigmoid -> split)
 //               -> transposed through a padded smem patch -> 128-byte coalesced row stores
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cmath>
 #include <vector>
 
 #include "../../include/payne_b200.h"
@@ -27,14 +40,16 @@
 
 namespace payne {
 
+enum { kModeT1 = 0, kModeT3 = 1, kModeX3 = 2 };
+
 struct TcWeights {
-  float* hi = nullptr;
-  float* lo = nullptr;
+  void* plane[3] = {nullptr, nullptr, nullptr};   // T: fp32 hi, lo ; X3: bf16 q1, q2, q3
+  void* xplane[3] = {nullptr, nullptr, nullptr};
+  float* scale = nullptr;                          // X3: per-row power of two
   int N = 0, K = 0;
 };
 struct TcActs {
-  float* hi = nullptr;
-  float* lo = nullptr;
+  void* plane[3] = {nullptr, nullptr, nullptr};    // sized for fp32; bf16 planes alias the storage
   long long rows = 0, ld = 0;
 };
 
@@ -84,10 +99,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -97,20 +119,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
-  return pred != 0;
 }
 }  // namespace ptx
 
@@ -124,41 +138,64 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M=128
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// fp32 accumulate, A and B K-major, M=128; fmt: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16)
+__host__ __device__ constexpr uint32_t umma_idesc(int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// fixed-point slices of the exact-accumulation split -----------------------------------------
+// activations (0 <= h < ~1): p1 = rint(h 2^8) 2^-8, p2 = rint(r1 2^16) 2^-16, p3 = rint(r2 2^24) 2^-24
+__device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bfloat16& p2, __nv_bfloat16& p3) {
+  const float a1 = rintf(h * 256.f) * (1.f / 256.f);
+  const float r1 = h - a1;
+  const float a2 = rintf(r1 * 65536.f) * (1.f / 65536.f);
+  const float r2 = r1 - a2;
+  const float a3 = rintf(r2 * 16777216.f) * (1.f / 16777216.f);
+  p1 = __float2bfloat16_rn(a1); p2 = __float2bfloat16_rn(a2); p3 = __float2bfloat16_rn(a3);
 }
 
 constexpr int kTcThreads = 256;
-constexpr int kBM = 128, kBK = 32;   // 32 tf32 = one 128-byte swizzle row
+constexpr int kBM = 128;
+constexpr int kRowBytes = 128;   // one swizzle row: 32 tf32 or 64 bf16 along K
 
-template <int BN, int NPROD>
+template <int BN, int MODE>
 struct TcCfg {
-  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
-  static constexpr int kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
+  static constexpr int kPlanes = MODE == kModeX3 ? 3 : (MODE == kModeT3 ? 2 : 1);
+  static constexpr int kElemBytes = MODE == kModeX3 ? 2 : 4;
+  static constexpr int kBK = kRowBytes / kElemBytes;              // K elements per stage
+  static constexpr int kUmmaK = 32 / kElemBytes;                  // K per MMA
+  static constexpr int kABytes = kBM * kRowBytes, kBBytes = BN * kRowBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kPatchBytes = 4 * 32 * 33 * 4;
   static constexpr int kBudget = 220 * 1024 - kPatchBytes - 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
   static constexpr int kSmem = kStages * kStageBytes + kPatchBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kAccCols = MODE == kModeX3 ? 2 * BN : BN;  // columns per accumulator set
+  static constexpr int kTmemCols = 2 * kAccCols;                  // double buffered
+  static_assert(kTmemCols <= 512, "TMEM budget");
+};
+
+struct TcMaps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
 };
 
 struct TcGemmArgs {
   const float* bias;
-  float* out0;          // EPI 0: fp32 C ; EPI 1: hi plane
-  float* out1;          // EPI 1: lo plane
+  const float* wscale;  // X3: per output column power-of-two scale
+  void* out0;           // EPI 0: fp32 C ; EPI 1: plane 0 of the next layer's operand
+  void* out1;
+  void* out2;
   long long ldc;
+  float bias_shift;     // EPI 0: added to the bias (-1 makes the layer emit line depth f - 1)
   int M, N, K;
 };
 
-template <int BN, int NPROD, int EPI>
+template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const __grid_constant__ TcGemmArgs G) {
-  using Cfg = TcCfg<BN, NPROD>;
-  constexpr int NS = Cfg::kStages;
+tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
+  using Cfg = TcCfg<BN, MODE>;
+  constexpr int NS = Cfg::kStages, NP = Cfg::kPlanes;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* stages = base;
@@ -173,11 +210,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (G.M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = (G.K + kBK - 1) / kBK;
+  const int num_kb = (G.K + Cfg::kBK - 1) / Cfg::kBK;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi);
-    if (NPROD == 3) { ptx::prefetch_tmap(&tmA_lo); ptx::prefetch_tmap(&tmB_lo); }
+    for (int p = 0; p < NP; ++p) { ptx::prefetch_tmap(&T.a[p]); ptx::prefetch_tmap(&T.b[p]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
@@ -191,7 +227,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer
+    // ===================== TMA producer: stage = [A planes][B planes]
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -200,12 +236,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ptx::mbar_wait(&empty[s], ph ^ 1);
           unsigned char* st = stages + s * Cfg::kStageBytes;
           ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
-          const int k0 = kb * kBK;
-          ptx::tma_load_2d(&tmA_hi, &full[s], st, k0, m0);
-          ptx::tma_load_2d(&tmB_hi, &full[s], st + Cfg::kPlanes * Cfg::kABytes, k0, n0);
-          if (NPROD == 3) {
-            ptx::tma_load_2d(&tmA_lo, &full[s], st + Cfg::kABytes, k0, m0);
-            ptx::tma_load_2d(&tmB_lo, &full[s], st + 2 * Cfg::kABytes + Cfg::kBBytes, k0, n0);
+          const int k0 = kb * Cfg::kBK;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            ptx::tma_load_2d(&T.a[p], &full[s], st + p * Cfg::kABytes, k0, m0);
+            ptx::tma_load_2d(&T.b[p], &full[s], st + NP * Cfg::kABytes + p * Cfg::kBBytes, k0, n0);
           }
           if (++s == NS) { s = 0; ph ^= 1; }
         }
@@ -214,31 +249,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BN);
+      constexpr uint32_t idesc = umma_idesc(BN, MODE == kModeX3 ? 1u : 2u);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], aph ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
+        const uint32_t d_corr = d_main + BN;               // X3 only
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
           const uint32_t st = ptx::smem_u32(stages + s * Cfg::kStageBytes);
-          const uint64_t a_hi = umma_desc_k_sw128(st);
-          const uint64_t a_lo = umma_desc_k_sw128(st + Cfg::kABytes);
-          const uint64_t b_hi = umma_desc_k_sw128(st + Cfg::kPlanes * Cfg::kABytes);
-          const uint64_t b_lo = umma_desc_k_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+          uint64_t da[3], db[3];
 #pragma unroll
-          for (int ks = 0; ks < kBK / 8; ++ks) {
-            const uint64_t koff = (uint64_t)((ks * 8 * 4) >> 4);   // 32 bytes per K=8 step
-            if (NPROD == 3) {
-              // small cross terms first, the dominant product last
-              ptx::mma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | ks) != 0);
-              ptx::mma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-              ptx::mma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1);
+          for (int p = 0; p < NP; ++p) {
+            da[p] = umma_desc_k_sw128(st + p * Cfg::kABytes);
+            db[p] = umma_desc_k_sw128(st + NP * Cfg::kABytes + p * Cfg::kBBytes);
+          }
+#pragma unroll
+          for (int ks = 0; ks < Cfg::kBK / Cfg::kUmmaK; ++ks) {
+            const uint64_t ko = (uint64_t)((ks * 32) >> 4);   // 32 bytes of K per MMA
+            const uint32_t first = (kb | ks) != 0;
+            if constexpr (MODE == kModeX3) {
+              ptx::mma_bf16(d_main, da[0] + ko, db[0] + ko, idesc, first);       // p1 q1 (exact)
+              ptx::mma_bf16(d_corr, da[0] + ko, db[2] + ko, idesc, first);       // p1 q3
+              ptx::mma_bf16(d_corr, da[1] + ko, db[1] + ko, idesc, 1);           // p2 q2
+              ptx::mma_bf16(d_corr, da[2] + ko, db[0] + ko, idesc, 1);           // p3 q1
+              ptx::mma_bf16(d_corr, da[0] + ko, db[1] + ko, idesc, 1);           // p1 q2
+              ptx::mma_bf16(d_corr, da[1] + ko, db[0] + ko, idesc, 1);           // p2 q1
+            } else if constexpr (MODE == kModeT3) {
+              ptx::mma_tf32(d_main, da[1] + ko, db[0] + ko, idesc, first);       // lo hi
+              ptx::mma_tf32(d_main, da[0] + ko, db[1] + ko, idesc, 1);           // hi lo
+              ptx::mma_tf32(d_main, da[0] + ko, db[0] + ko, idesc, 1);           // hi hi
             } else {
-              ptx::mma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | ks) != 0);
+              ptx::mma_tf32(d_main, da[0] + ko, db[0] + ko, idesc, first);
             }
           }
           ptx::mma_commit(&empty[s]);                  // frees the ring slot when the MMAs retire
@@ -258,31 +303,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
       const int row_base = m0 + q * 32;
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col0 = n0 + ch * 32;
         if (col0 >= G.N) break;
         uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+        ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
+        if constexpr (MODE == kModeX3) {
+          uint32_t c[32];
+          ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pt[lane * 33 + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) pt[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(c[j]);
+        } else {
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pt[lane * 33 + j] = __uint_as_float(v[j]);
+        }
         __syncwarp();
         const int gcol = col0 + lane;
         const bool colok = gcol < G.N;
-        const float bv = colok ? __ldg(G.bias + gcol) : 0.f;
+        float bv = colok ? __ldg(G.bias + gcol) : 0.f;
+        if (EPI == 0) bv += G.bias_shift;
+        const float sc = (MODE == kModeX3 && colok) ? __ldg(G.wscale + gcol) : 1.f;
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
           const int grow = row_base + r;
           if (grow >= G.M) break;
-          float val = pt[r * 33 + lane] + bv;
+          float val = fmaf(pt[r * 33 + lane], sc, bv);
           if (colok) {
+            const long long o = (long long)grow * G.ldc + gcol;
             if (EPI == 0) {
-              G.out0[(long long)grow * G.ldc + gcol] = val;
+              ((float*)G.out0)[o] = val;
             } else {
               val = sigmoidf_exact(val);
-              const float hi = ptx::to_tf32(val);
-              G.out0[(long long)grow * G.ldc + gcol] = hi;
-              G.out1[(long long)grow * G.ldc + gcol] = ptx::to_tf32(val - hi);
+              if constexpr (MODE == kModeX3) {
+                __nv_bfloat16 p1, p2, p3;
+                x3_split_act(val, p1, p2, p3);
+                ((__nv_bfloat16*)G.out0)[o] = p1; ((__nv_bfloat16*)G.out1)[o] = p2; ((__nv_bfloat16*)G.out2)[o] = p3;
+              } else {
+                const float hi = ptx::to_tf32(val);
+                ((float*)G.out0)[o] = hi;
+                ((float*)G.out1)[o] = ptx::to_tf32(val - hi);
+              }
             }
           }
         }
@@ -299,7 +363,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// fp32 -> (hi, lo) TF32 planes
+// fp32 -> operand planes of the next GEMM
 __global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, float* __restrict__ hi,
                                   float* __restrict__ lo, long long ldd, long long rows, int cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,6 +373,16 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, 
   const float h = ptx::to_tf32(x);
   hi[r * ldd + c] = h;
   lo[r * ldd + c] = ptx::to_tf32(x - h);
+}
+__global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ p1,
+                                __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldd,
+                                long long rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols; const int c = (int)(i % cols);
+  __nv_bfloat16 a, b, d;
+  x3_split_act(src[r * lds + c], a, b, d);
+  p1[r * ldd + c] = a; p2[r * ldd + c] = b; p3[r * ldd + c] = d;
 }
 
 // ------------------------------------------------------------------ host side
@@ -329,97 +403,152 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// 2-D fp32 row-major [rows, K] (pitch ld floats) -> boxes of {32 floats, box_rows}, 128B swizzle
-inline int make_tmap(CUtensorMap* m, const float* ptr, long long rows, int K, long long ld, int box_rows) {
+// 2-D row-major [rows, K] (pitch ld elements) -> boxes of {128 bytes of K, box_rows}, 128B swizzle
+inline int make_tmap(CUtensorMap* m, const void* ptr, long long rows, int K, long long ld, int box_rows,
+                     int elem_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return PAYNE_E_CUDA;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
-inline int tc_prepare_weights(TcWeights* w, const float* W_dev, int N, int K, std::vector<void*>* owned) {
+// Host-side split of a weight matrix (done once per context).
+inline int tc_prepare_weights(TcWeights* w, const float* W_host, int N, int K, std::vector<void*>* owned) {
   w->N = N; w->K = K;
-  if (K % 4 != 0) return PAYNE_OK;   // not TMA-addressable; tc_run_layers refuses this layer
+  if (K % 8 != 0) return PAYNE_OK;   // not TMA-addressable; tc_run_layers refuses this layer
   const size_t n = (size_t)N * K;
-  if (cudaMalloc((void**)&w->hi, n * 4) != cudaSuccess) return PAYNE_E_NOMEM;
-  owned->push_back(w->hi);
-  if (cudaMalloc((void**)&w->lo, n * 4) != cudaSuccess) return PAYNE_E_NOMEM;
-  owned->push_back(w->lo);
-  tf32_split_kernel<<<(unsigned)((n + 255) / 256), 256>>>(W_dev, K, w->hi, w->lo, K, N, K);
-  return cudaDeviceSynchronize() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
+  std::vector<float> hi(n), lo(n), sc(N);
+  std::vector<uint16_t> q[3] = {std::vector<uint16_t>(n), std::vector<uint16_t>(n), std::vector<uint16_t>(n)};
+  auto tf32 = [](float x) {   // cvt.rna.tf32: round to nearest, ties away, 10-bit mantissa
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u += 0x1000u; u &= 0xFFFFE000u;
+    float r; memcpy(&r, &u, 4); return r;
+  };
+  auto bf16bits = [](float x) { uint32_t u; memcpy(&u, &x, 4); return (uint16_t)(u >> 16); };   // exact by construction
+  for (int r = 0; r < N; ++r) {
+    float mx = 0.f;
+    for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(W_host[(size_t)r * K + k]));
+    int e = 0;
+    float s = 1.f;
+    if (mx > 0.f && std::isfinite(mx)) { std::frexp(mx, &e); s = std::ldexp(1.f, e); }
+    sc[r] = s;
+    for (int k = 0; k < K; ++k) {
+      const size_t i = (size_t)r * K + k;
+      const float x = W_host[i];
+      hi[i] = tf32(x); lo[i] = tf32(x - hi[i]);
+      const float u = x / s;                                            // exact (power of two)
+      const float a1 = std::nearbyint(u * 128.f) / 128.f;
+      const float r1 = u - a1;
+      const float a2 = std::nearbyint(r1 * 32768.f) / 32768.f;
+      const float r2 = r1 - a2;
+      const float a3 = std::nearbyint(r2 * 8388608.f) / 8388608.f;
+      q[0][i] = bf16bits(a1); q[1][i] = bf16bits(a2); q[2][i] = bf16bits(a3);
+    }
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (cudaMalloc(dst, bytes) != cudaSuccess) return PAYNE_E_NOMEM;
+    owned->push_back(*dst);
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
+  };
+  int rc = up(&w->plane[0], hi.data(), n * 4); if (rc) return rc;
+  rc = up(&w->plane[1], lo.data(), n * 4); if (rc) return rc;
+  for (int p = 0; p < 3; ++p) { rc = up(&w->xplane[p], q[p].data(), n * 2); if (rc) return rc; }
+  rc = up((void**)&w->scale, sc.data(), (size_t)N * 4);
+  return rc;
 }
 
 inline int tc_alloc_acts(TcActs* a, long long rows, long long ld) {
   a->rows = rows; a->ld = ld;
-  if (cudaMalloc((void**)&a->hi, (size_t)rows * ld * 4) != cudaSuccess) return PAYNE_E_NOMEM;
-  if (cudaMalloc((void**)&a->lo, (size_t)rows * ld * 4) != cudaSuccess) return PAYNE_E_NOMEM;
+  for (int p = 0; p < 3; ++p)
+    if (cudaMalloc(&a->plane[p], (size_t)rows * ld * 4) != cudaSuccess) return PAYNE_E_NOMEM;
   return PAYNE_OK;
 }
 inline void tc_free_acts(TcActs* a) {
-  if (a->hi) cudaFree(a->hi);
-  if (a->lo) cudaFree(a->lo);
-  a->hi = a->lo = nullptr; a->rows = 0;
+  for (int p = 0; p < 3; ++p) { if (a->plane[p]) cudaFree(a->plane[p]); a->plane[p] = nullptr; }
+  a->rows = 0;
 }
 
-template <int BN, int NPROD, int EPI>
-inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, float* out0, float* out1,
-                     long long ldc, int M, int sm_count, cudaStream_t st) {
-  using Cfg = TcCfg<BN, NPROD>;
+template <int BN, int MODE, int EPI>
+inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
+                     void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+  using Cfg = TcCfg<BN, MODE>;
   static_assert(Cfg::kStages >= 2, "ring too shallow");
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  if (make_tmap(&ta_hi, A.hi, M, K, A.ld, kBM)) return PAYNE_E_CUDA;
-  if (make_tmap(&ta_lo, A.lo, M, K, A.ld, kBM)) return PAYNE_E_CUDA;
-  if (make_tmap(&tb_hi, W.hi, W.N, K, K, BN)) return PAYNE_E_CUDA;
-  if (make_tmap(&tb_lo, W.lo, W.N, K, K, BN)) return PAYNE_E_CUDA;
+  TcMaps T;
+  for (int p = 0; p < Cfg::kPlanes; ++p) {
+    const void* wp = MODE == kModeX3 ? W.xplane[p] : W.plane[p];
+    if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.b[p], wp, W.N, K, K, BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+  }
+  for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, NPROD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmem) != cudaSuccess) return PAYNE_E_CUDA;
     attr_set = true;
   }
-  TcGemmArgs G{bias, out0, out1, ldc, M, W.N, K};
+  TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K};
   const int tiles = ((M + kBM - 1) / kBM) * ((W.N + BN - 1) / BN);
   const int grid = tiles < sm_count ? tiles : sm_count;
-  tc_gemm_kernel<BN, NPROD, EPI><<<grid, kTcThreads, Cfg::kSmem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, G);
+  tc_gemm_kernel<BN, MODE, EPI><<<grid, kTcThreads, Cfg::kSmem, st>>>(T, G);
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
-// lin2..lin6 from the fp32 output of lin1 (h1, pitch = dims_out[0]).
-inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
-                         const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
-                         int prec, int sm_count, cudaStream_t st, long long* launches) {
-  if (prec != PAYNE_PREC_PARITY_3XTF32 && prec != PAYNE_PREC_TF32) return PAYNE_E_UNSUPPORTED;
-  for (int k = 1; k < 6; ++k)
-    if (!tcw[k].hi) return PAYNE_E_UNSUPPORTED;
-  {
-    const long long tot = (long long)nb * dims_out[0];
-    tf32_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h1, dims_out[0], actA->hi, actA->lo,
-                                                                      actA->ld, nb, dims_out[0]);
-    ++*launches;
-  }
+template <int MODE>
+inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
+                              const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
+                              float bias_shift, int sm_count, cudaStream_t st, long long* launches) {
+  const long long tot = (long long)nb * dims_out[0];
+  const unsigned blocks = (unsigned)((tot + 255) / 256);
+  if (MODE == kModeX3)
+    x3_split_kernel<<<blocks, 256, 0, st>>>(h1, dims_out[0], (__nv_bfloat16*)actA->plane[0],
+                                            (__nv_bfloat16*)actA->plane[1], (__nv_bfloat16*)actA->plane[2],
+                                            actA->ld, nb, dims_out[0]);
+  else
+    tf32_split_kernel<<<blocks, 256, 0, st>>>(h1, dims_out[0], (float*)actA->plane[0], (float*)actA->plane[1],
+                                              actA->ld, nb, dims_out[0]);
+  ++*launches;
   TcActs* cur = actA; TcActs* nxt = actB;
   int rc = PAYNE_OK;
   for (int k = 1; k < 5 && !rc; ++k) {
-    if (prec == PAYNE_PREC_PARITY_3XTF32)
-      rc = tc_launch<64, 3, 1>(*cur, dims_in[k], tcw[k], bias[k], nxt->hi, nxt->lo, nxt->ld, nb, sm_count, st);
-    else
-      rc = tc_launch<64, 1, 1>(*cur, dims_in[k], tcw[k], bias[k], nxt->hi, nxt->lo, nxt->ld, nb, sm_count, st);
+    rc = tc_launch<64, MODE, 1>(*cur, dims_in[k], tcw[k], bias[k], nxt->plane[0], nxt->plane[1], nxt->plane[2],
+                                nxt->ld, 0.f, nb, sm_count, st);
     ++*launches;
     TcActs* t = cur; cur = nxt; nxt = t;
   }
   if (rc) return rc;
-  if (prec == PAYNE_PREC_PARITY_3XTF32)
-    rc = tc_launch<256, 3, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, ldo, nb, sm_count, st);
-  else
-    rc = tc_launch<256, 1, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, ldo, nb, sm_count, st);
+  rc = tc_launch<128, MODE, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, nullptr, ldo, bias_shift, nb,
+                               sm_count, st);
   ++*launches;
   return rc;
+}
+
+// lin2..lin6 from the fp32 output of lin1 (h1, pitch = dims_out[0]).  bias_shift is added to the
+// last layer's bias (the likelihood path asks for line depth f - 1 with bias_shift = -1).
+inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
+                         const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
+                         float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches) {
+  for (int k = 1; k < 6; ++k)
+    if (!tcw[k].plane[0]) return PAYNE_E_UNSUPPORTED;
+  switch (prec) {
+    case PAYNE_PREC_PARITY:
+      return tc_run_layers_mode<kModeX3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
+                                         sm_count, st, launches);
+    case PAYNE_PREC_3XTF32:
+      return tc_run_layers_mode<kModeT3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
+                                         sm_count, st, launches);
+    case PAYNE_PREC_TF32:
+      return tc_run_layers_mode<kModeT1>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
+                                         sm_count, st, launches);
+    default:
+      return PAYNE_E_UNSUPPORTED;
+  }
 }
 
 }  // namespace payne

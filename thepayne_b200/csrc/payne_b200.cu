@@ -75,6 +75,28 @@ void interp_entry(const std::vector<double>& xp, double x, bool nan_outside, int
   *t = (float)((x - xp[k]) / (xp[k + 1] - xp[k]));
 }
 
+// exp(i a) rounded to floats with the modulus as close to 1 as the float grid allows: among the
+// neighbouring floats of cos a and sin a pick the pair minimising | |W|^2 - 1 |.  Plain rounding
+// leaves a table whose mean |W|^2 - 1 is a few 1e-9 negative; every element meets ~6 twiddles
+// per transform pair, so that becomes a coherent -1.4e-8 amplitude loss per convolution.
+float2 unit_round(double a) {
+  const double c = std::cos(a), s = std::sin(a);
+  const float cf = (float)c, sf = (float)s;
+  const float cc[3] = {cf, std::nextafter(cf, INFINITY), std::nextafter(cf, -INFINITY)};
+  const float ss[3] = {sf, std::nextafter(sf, INFINITY), std::nextafter(sf, -INFINITY)};
+  const double uc = std::fabs((double)std::nextafter(std::fabs(cf), INFINITY) - std::fabs((double)cf));
+  const double us = std::fabs((double)std::nextafter(std::fabs(sf), INFINITY) - std::fabs((double)sf));
+  float bc = cf, bs = sf;
+  double best = std::fabs((double)cf * cf + (double)sf * sf - 1.0);
+  for (float x : cc)
+    for (float y : ss) {
+      if (std::fabs((double)x - c) > uc || std::fabs((double)y - s) > us) continue;
+      const double e = std::fabs((double)x * x + (double)y * y - 1.0);
+      if (e < best) { best = e; bc = x; bs = y; }
+    }
+  return make_float2(bc, bs);
+}
+
 // sb(u) of smoothing.py:612-619 without the small-u cancellation
 double rot_sb(double u) {
   u = std::fabs(u);
@@ -234,8 +256,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   // twiddles
   std::vector<float2> tw(N1 / 2);
   for (int e = 0; e < N1 / 2; ++e) {
-    const double a = -2.0 * 3.14159265358979323846 * (double)e / (double)N1;
-    tw[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+    tw[e] = unit_round(-2.0 * 3.14159265358979323846 * (double)e / (double)N1);
   }
   float2* dtw;
   rc = upload_owned(c, &dtw, tw.data(), tw.size()); if (rc) return rc;
@@ -302,24 +323,20 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
       worst = std::max(worst, std::fabs(((double)k + ta) - ((double)back[i].x + (double)te)));
     }
     c->use_fast = (worst < 2e-7) && l2 >= 10 && l2 <= 15;
-    std::vector<double> oq(no);
-    std::vector<float> ois(no), oot(no);
+    std::vector<double> oq(no), oot(no);
     for (int j = 0; j < no; ++j) {
       oq[j] = (lnw[j] - T.lnw0) * F.inv_dlnw;
-      ois[j] = (float)(1.0 / obs->eflux[j]);
-      oot[j] = (float)((obs->flux[j] - 1.0) / obs->eflux[j]);
+      oot[j] = (obs->flux[j] - 1.0) / obs->eflux[j];
     }
-    double* dq; float *dis, *dot;
+    double *dq, *dot;
     rc = upload_owned(c, &dq, oq.data(), no); if (rc) return rc;
-    rc = upload_owned(c, &dis, ois.data(), no); if (rc) return rc;
     rc = upload_owned(c, &dot, oot.data(), no); if (rc) return rc;
-    F.obs_q = dq; F.obs_inv_s_f = dis; F.obs_ot_f = dot;
+    F.obs_q = dq; F.obs_otm1 = dot;
     for (int set = 0; set < 2; ++set)
       for (int ip = 0; ip < 4; ++ip)
         for (int q = 0; q < 16; ++q) {
           const double M = (double)(1 << (13 + set));
-          const double a = -2.0 * 3.14159265358979323846 * (double)ip * (double)kNT * (double)q / M;
-          F.twc.c[set][ip][q] = make_float2((float)std::cos(a), (float)std::sin(a));
+          F.twc.c[set][ip][q] = unit_round(-2.0 * 3.14159265358979323846 * (double)ip * (double)kNT * (double)q / M);
         }
   }
   if (c->use_fast) {
@@ -350,7 +367,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   c->tail_grid = occ * c->sm_count;
   // tensor-core operand copies of the weights
   for (int k = 1; k < 6; ++k) {
-    rc = payne::tc_prepare_weights(&c->tcw[k], c->W[k], dout[k], din[k], &c->owned);
+    rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
     if (rc) return fail(rc, "tc_prepare_weights failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
   }
   return PAYNE_OK;
@@ -400,7 +417,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
   c->flux = c->hA = c->hB = nullptr; c->chi2_sed = nullptr; c->slab_alloc = 0;
   const long long rows = (need + 127) / 128 * 128;
   if (c->has_spec) {
-    const long long hmax = std::max({c->H[0], c->H[1], c->H[2]});
+    const long long hmax = (std::max({c->H[0], c->H[1], c->H[2]}) + 7) / 8 * 8;
     CU_TRY(cudaMalloc((void**)&c->flux, (size_t)rows * c->ldf * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
@@ -413,8 +430,10 @@ int ensure_workspace(PayneCtx* c, long long B) {
 }
 
 // emulator forward for `nb` rows: labels gathered from x (ld) by E -> out [nb, ldo] fp32
+// want_depth: the tensor-core modes emit f - 1 (bias shifted by -1 in the epilogue) so that the
+// tail keeps ~8 more mantissa bits of the line depth; *is_depth reports what was written.
 int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long long ld, int nb,
-            float* out, long long ldo, cudaStream_t st) {
+            float* out, long long ldo, bool want_depth, int* is_depth, cudaStream_t st) {
   using namespace payne;
   const int prec = c->lay.precision;
   {
@@ -423,6 +442,7 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
                                                                          c->H[0], nb);
     c->launches++;
   }
+  *is_depth = 0;
   if (prec == PAYNE_PREC_SIMT_FP32) {
     float* cur = c->hA; float* nxt = c->hB;
     for (int k = 1; k < 6; ++k) {
@@ -438,7 +458,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
     }
   } else {
     int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, c->hA, &c->actA, &c->actB, nb, out, ldo,
-                           prec, c->sm_count, st, &c->launches);
+                           want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches);
+    *is_depth = want_depth ? 1 : 0;
     if (rc) return fail(rc, "tensor-core MLP path failed (precision " + std::to_string(prec) + ")");
   }
   CU_TRY(cudaGetLastError());
@@ -462,8 +483,9 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       for (auto& e : evs) CU_TRY(cudaEventCreate(&e));
       CU_TRY(cudaEventRecord(evs[0], st));
     }
+    int is_depth = 0;
     if (c->has_spec) {
-      rc = run_mlp(c, c->enc, th, ld, nb, c->flux, c->ldf, st);
+      rc = run_mlp(c, c->enc, th, ld, nb, c->flux, c->ldf, true, &is_depth, st);
       if (rc) return rc;
     }
     if (c->timing) CU_TRY(cudaEventRecord(evs[1], st));
@@ -477,7 +499,7 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
     if (c->timing) CU_TRY(cudaEventRecord(evs[2], st));
     if (c->has_spec) {
       TailParams T = c->tail;
-      T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb;
+      T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb; T.flux_is_depth = is_depth;
       T.chi2_sed = c->has_phot ? c->chi2_sed : nullptr;
       T.lnl = lnl ? lnl + p0 : nullptr;
       T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
@@ -611,7 +633,8 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
   for (int i = 0; i < E.D_in; ++i) E.col[i] = i;
   for (long long p0 = 0; p0 < B; p0 += c->slab) {
     const int nb = (int)std::min<long long>(c->slab, B - p0);
-    rc = run_mlp(c, E, x_dev + p0 * c->D_in, c->D_in, nb, y_dev + p0 * ldy, ldy, (cudaStream_t)stream);
+    int isd = 0;
+    rc = run_mlp(c, E, x_dev + p0 * c->D_in, c->D_in, nb, y_dev + p0 * ldy, ldy, false, &isd, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return PAYNE_OK;
@@ -644,7 +667,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   if (!c || !key) return fail(PAYNE_E_INVALID, "null argument");
   std::string k(key);
   if (k == "precision") {
-    if (value < 0 || value > 3) return fail(PAYNE_E_INVALID, "unknown precision");
+    if (value < 0 || value > 4 || value == PAYNE_PREC_BF16) return fail(PAYNE_E_INVALID, "unknown precision");
     c->lay.precision = (int)value;
     return PAYNE_OK;
   }
@@ -656,6 +679,50 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
   return fail(PAYNE_E_INVALID, "unknown key " + k);
+}
+
+int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_host, int M, int N, int K,
+                    int precision, int device, float* C_host) {
+  using namespace payne;
+  if (!A_host || !W_host || !bias_host || !C_host || M < 1 || N < 1 || K < 8) return fail(PAYNE_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  std::vector<void*> owned;
+  TcWeights w;
+  int rc = tc_prepare_weights(&w, W_host, N, K, &owned);
+  TcActs a;
+  const long long rows = (M + 127) / 128 * 128, ld = (K + 7) / 8 * 8;
+  float *dA = nullptr, *dC = nullptr, *db = nullptr;
+  if (!rc && !w.plane[0]) rc = fail(PAYNE_E_UNSUPPORTED, "K must be a multiple of 8");
+  if (!rc) rc = tc_alloc_acts(&a, rows, ld);
+  if (!rc && (cudaMalloc((void**)&dA, (size_t)M * K * 4) != cudaSuccess ||
+              cudaMalloc((void**)&dC, (size_t)M * N * 4) != cudaSuccess ||
+              cudaMalloc((void**)&db, (size_t)N * 4) != cudaSuccess)) rc = fail(PAYNE_E_NOMEM, "gemm_test alloc");
+  if (!rc) {
+    cudaMemcpy(dA, A_host, (size_t)M * K * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bias_host, (size_t)N * 4, cudaMemcpyHostToDevice);
+    const unsigned blocks = (unsigned)(((long long)M * K + 255) / 256);
+    if (precision == PAYNE_PREC_PARITY) {
+      x3_split_kernel<<<blocks, 256>>>(dA, K, (__nv_bfloat16*)a.plane[0], (__nv_bfloat16*)a.plane[1],
+                                       (__nv_bfloat16*)a.plane[2], a.ld, M, K);
+      rc = tc_launch<128, kModeX3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
+    } else {
+      tf32_split_kernel<<<blocks, 256>>>(dA, K, (float*)a.plane[0], (float*)a.plane[1], a.ld, M, K);
+      if (precision == PAYNE_PREC_3XTF32)
+        rc = tc_launch<128, kModeT3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
+      else if (precision == PAYNE_PREC_TF32)
+        rc = tc_launch<128, kModeT1, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
+      else rc = PAYNE_E_UNSUPPORTED;
+    }
+    if (rc) fail(rc, "gemm_test launch failed");
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(PAYNE_E_CUDA, cudaGetErrorString(cudaGetLastError()));
+    if (!rc) cudaMemcpy(C_host, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+  }
+  tc_free_acts(&a);
+  if (dA) cudaFree(dA); if (dC) cudaFree(dC); if (db) cudaFree(db);
+  for (void* p : owned) cudaFree(p);
+  return rc;
 }
 
 double payne_ctx_last_ms(PayneCtx* c, int which) {

@@ -64,6 +64,7 @@ struct TailParams {
   long long ld;
   float* flux;              // [B, ldf] emulator output; scratch, overwritten
   long long ldf;
+  int flux_is_depth;        // rows hold f - 1 (tensor-core path) instead of f
   const double* chi2_sed;   // [B] or null
   double* lnl;              // [B] or null
   double* model_out;        // [B, n_obs] or null
@@ -161,9 +162,8 @@ __device__ __forceinline__ double chebval_dev(double x, const double* c, int nc)
 }
 
 __device__ __forceinline__ float depth_of(float v, bool is_depth, bool fill_nan) {
-  if (is_depth) return v;
   if (fill_nan && v != v) return 0.f;   // nan_to_num(nan=1.0) (smoothing.py:138) in depth space
-  return v - 1.f;
+  return is_depth ? v : v - 1.f;
 }
 
 __device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S) {
@@ -246,7 +246,7 @@ tail_kernel(const __grid_constant__ TailParams P) {
       __syncthreads();
       continue;
     }
-    bool is_depth = false;
+    bool is_depth = P.flux_is_depth != 0;
 
     // ---------------- stage 1: rotational broadening on the full emulator grid
     if (S.do_rot) {
@@ -254,7 +254,7 @@ tail_kernel(const __grid_constant__ TailParams P) {
       for (int k = tid; k < N1; k += kTailThreads) {
         const int2 e = __ldg(P.fwd1 + k);
         const float t = __int_as_float(e.y);
-        const float a = depth_of(row[e.x], false, true), b = depth_of(row[e.x + 1], false, true);
+        const float a = depth_of(row[e.x], is_depth, true), b = depth_of(row[e.x + 1], is_depth, true);
         zf[zidx(k)] = a + t * (b - a);
       }
       __syncthreads();

@@ -26,8 +26,7 @@ struct FastGrid {
   float c_grid1;                      // du1 / 2    (source spacing = stage-1 grid)
   double dlnw, inv_dlnw;
   const double* obs_q;                // [n_obs] (ln lambda_j - ln w_0) / dlnw
-  const float* obs_inv_s_f;           // [n_obs] 1/eflux
-  const float* obs_ot_f;              // [n_obs] (flux - 1)/eflux
+  const double* obs_otm1;             // [n_obs] (flux - 1)/eflux : r = depth/eflux - otm1
   TwConst twc;
 };
 
@@ -86,7 +85,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       __syncthreads();
       continue;
     }
-    bool is_depth = false;
+    bool is_depth = P.flux_is_depth != 0;
 
     // ---------------- stage 1: rotational broadening on the full emulator grid
     if (S.do_rot) {
@@ -98,7 +97,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
         for (int k = tid; k < N1; k += kNT) {
           int jj = j; float dl = (float)rem * F.f_invden;
           if (jj >= n - 1) { jj = n - 2; dl = 1.f; }
-          const float a = depth_of(row[jj], false, true), b = depth_of(row[jj + 1], false, true);
+          const float a = depth_of(row[jj], is_depth, true), b = depth_of(row[jj + 1], is_depth, true);
           zf[zidx(k)] = fmaf(interp_w(dl, F.c_native), b - a, a);
           j += F.f_incj; rem += F.f_incr;
           if (rem >= F.f_den) { rem -= F.f_den; ++j; }
@@ -171,16 +170,16 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
 #pragma unroll 4
         for (int j = tid; j < P.n_obs; j += kNT) {
           const double pp = (__ldg(F.obs_q + j) - q0) * scale;
-          float r;
-          if (!(pp >= 0.0 && pp <= pmax)) r = CUDART_NAN_F;        // smoothing.py:289 left/right = nan
+          double r;
+          if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
           else {
             const int k = min((int)pp, N2 - 2);
             const float dl = (float)(pp - (double)k);
             const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
             const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
-            r = fmaf(d, __ldg(F.obs_inv_s_f + j), -__ldg(F.obs_ot_f + j));
+            r = fma((double)d, __ldg(P.obs_inv_s + j), -__ldg(F.obs_otm1 + j));
           }
-          acc = fma((double)r, (double)r, acc);
+          acc = fma(r, r, acc);
         }
       } else {
         for (int j = tid; j < P.n_obs; j += kNT) {

@@ -6,27 +6,30 @@ from conftest import load_case
 from oracle import payne_oracle as O
 from thepayne_b200.engine import engine_from_config
 cfg, g = load_case('c2')
-eng = engine_from_config(cfg, precision='simt')
 L = O.OracleLikelihood(cfg)
-base = g['theta'][13].copy()
 ix = {p: i for i, p in enumerate(cfg.fitpars_i)}
 rows = []
-for v in [0.0, 0.05, 0.3, 0.735, 1.5, 3.0, 6.0, 12.0]:
-    r = base.copy(); r[ix['Vrot']] = v; rows.append(r)
-r = g['theta'][7].copy(); rows.append(r)
+for vr, R in [(0.0, np.nan), (1.3, np.nan), (0.0, 32653.0), (1.3, 32653.0), (6.0, np.nan), (6.0, 32653.0)]:
+    r = g['theta'][7].copy(); r[ix['Vrot']] = vr; r[ix['Inst_R']] = R; rows.append(r)
 th = np.array(rows)
-flux, _, lnl = eng.model_batch(torch.from_numpy(th).cuda())
-flux = flux.cpu().numpy()
-x = th[:, :4]
-y = eng.ann_eval(x).cpu().numpy()
-for i in range(len(th)):
-    fo, _ = L.model(th[i], mlp_flux=y[i].astype(np.float32).copy())
-    d = flux[i] - fo
-    j = np.argmax(np.abs(d))
-    lt = -0.5 * np.sum(((fo - cfg.obs_flux) / cfg.obs_eflux) ** 2)
-    print('vrot %6.3f vrad %6.2f: dlnL %+.2e  flux err rms %.2e max %.2e at pix %d  mean %+.2e  corr(d, resid) %.3f' % (
-        th[i, ix['Vrot']], th[i, ix['Vrad']], lnl[i].item() - lt, d.std(), np.abs(d).max(), j, d.mean(),
-        np.corrcoef(d, fo - cfg.obs_flux)[0, 1]))
-    if i in (3, 8):
-        print('    err[::700]', np.array2string(d[::700], precision=2))
-        k = np.argsort(-np.abs(d))[:8]; print('    worst pixels', sorted(k.tolist()))
+for fast in (1, 0):
+    eng = engine_from_config(cfg, precision='simt')
+    eng.set('fast_tail', fast)
+    flux, _, lnl = eng.model_batch(torch.from_numpy(th).cuda())
+    flux = flux.cpu().numpy()
+    y = eng.ann_eval(th[:, :4]).cpu().numpy()
+    print('fast_tail', fast)
+    for i in range(len(th)):
+        fo, _ = L.model(th[i], mlp_flux=y[i].astype(np.float32).copy())
+        e = flux[i] - fo
+        resid = fo - cfg.obs_flux
+        d = fo - 1.0
+        b = np.stack([d, np.gradient(fo), np.gradient(np.gradient(fo)), np.ones_like(fo)], 1)
+        c, *_ = np.linalg.lstsq(b, e, rcond=None)
+        s2 = 1.0 / cfg.obs_eflux ** 2
+        dl_tot = -np.sum(resid * e * s2)
+        parts = [-np.sum(resid * (c[k] * b[:, k]) * s2) for k in range(4)]
+        print(' R %7.0f vrot %8.1e vrad %6.1f dlnL(lin) %+.2e | amp c=%+.2e -> %+.2e | shift c=%+.2e px -> %+.2e | width c=%+.2e -> %+.2e | const c=%+.2e -> %+.2e | rms e %.2e resid-fit %.2e' % (
+            th[i, ix['Inst_R']], th[i, ix['Vrot']], th[i, ix['Vrad']], dl_tot, c[0], parts[0], c[1], parts[1], c[2], parts[2], c[3], parts[3],
+            e.std(), (e - b @ c).std()))
+    eng.close()
