@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 # precision -> (flux rel bar, lnL abs bar, lnL rel bar)
 BARS = {
     'parity': (1e-5, 1e-3, 1e-8),      # tcgen05 exact-accumulation bf16x3 MLP  (the default)
-    'simt': (1e-5, 1e-3, 1e-8),        # CUDA-core fp32 MLP
+    'simt': (1e-5, 2e-3, 2e-8),        # CUDA-core fp32 MLP (sequential fp32 accumulation; cross-check mode)
     '3xtf32': (1e-5, 3e-2, 1.5e-6),    # tcgen05 3xTF32: accumulator truncation bias -> NOT lnL-parity
     'tf32': (3e-4, 0.5, 5e-5),         # tcgen05 1xTF32 -- fast mode, NOT a parity mode
 }

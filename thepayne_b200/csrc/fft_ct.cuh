@@ -87,8 +87,10 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
     const int b = g >> LOG2S, j = g & (S - 1);
     const int base = (b << LOG2L) + j;
     float2 v[R];
+    // stride >= 128 points: adding m*S never touches the bits the swizzle reads or flips
+    const int sbase = swz(base);
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = z[swz(base + (m << LOG2S))];
+    for (int m = 0; m < R; ++m) v[m] = (LOG2S >= 7) ? z[sbase + (m << LOG2S)] : z[swz(base + (m << LOG2S))];
     constexpr int kSet = LOG2M >= 13 ? LOG2M - 13 : 0;
     const int ip = i % SPAN;
     if constexpr (!INV) {
@@ -109,7 +111,10 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
       dftR<R, true>(v);
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) z[swz(base + (m << LOG2S))] = v[m];
+    for (int m = 0; m < R; ++m) {
+      if (LOG2S >= 7) z[sbase + (m << LOG2S)] = v[m];
+      else z[swz(base + (m << LOG2S))] = v[m];
+    }
   }
 }
 

@@ -44,7 +44,7 @@ template <bool SIGMOID>
 __global__ void __launch_bounds__(256)
 sgemm_bias_act_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W,
                       const float* __restrict__ bias, float* __restrict__ C, long long ldc,
-                      int M, int N, int K) {
+                      int M, int N, int K, float bias_shift) {
   constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
   __shared__ float As[BK][BM + PAD];
   __shared__ float Ws[BK][BN + PAD];
@@ -86,7 +86,7 @@ sgemm_bias_act_kernel(const float* __restrict__ A, long long lda, const float* _
     for (int j = 0; j < 8; ++j) {
       const int gn = n0 + tx * 8 + j;
       if (gn >= N) continue;
-      float v = acc[i][j] + __ldg(bias + gn);
+      float v = acc[i][j] + (__ldg(bias + gn) + bias_shift);
       if (SIGMOID) v = sigmoidf_exact(v);
       C[(long long)gm * ldc + gn] = v;
     }

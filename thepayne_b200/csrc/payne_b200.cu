@@ -289,6 +289,8 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   for (int i = 0; i < PAYNE_NPAR; ++i) { T.col[i] = c->lay.col[i]; T.fixed[i] = c->lay.fixed[i]; }
   T.n_poly = c->lay.modpoly_bool ? c->lay.n_poly : 0;
   for (int i = 0; i < PAYNE_MAX_POLY; ++i) T.poly_col[i] = c->lay.poly_col[i];
+  T.n_labels = s->D_in;
+  for (int i = 0; i < 8; ++i) { T.label_col[i] = E.col[i]; T.label_fixed[i] = E.fixed[i]; }
   c->ldf = ((long long)n + 3) / 4 * 4;
 
   // ---- analytic regrid constants for the fast tail, verified against the exact tables
@@ -297,8 +299,8 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     const double dlnw = (std::log(w[n - 1]) - std::log(w[0])) / (double)(n - 1);
     F.dlnw = dlnw; F.inv_dlnw = 1.0 / dlnw;
     F.f_num = n - 1; F.f_den = N1 - 1;
-    F.f_incj = (int)(((long long)kNT * F.f_num) / F.f_den);
-    F.f_incr = (int)(((long long)kNT * F.f_num) % F.f_den);
+    F.f_incj = (int)((2LL * kNT * F.f_num) / F.f_den);       // forward regrid walks in pairs
+    F.f_incr = (int)((2LL * kNT * F.f_num) % F.f_den);
     F.b_num = N1 - 1; F.b_den = n - 1;
     F.b_incj = (int)(((long long)kNT * F.b_num) / F.b_den);
     F.b_incr = (int)(((long long)kNT * F.b_num) % F.b_den);
@@ -449,10 +451,12 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
       const int K = c->dims_in[k], N = c->dims_out[k];
       dim3 grid((N + 127) / 128, (nb + 127) / 128);
       if (k < 5) {
-        sgemm_bias_act_kernel<true><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K);
+        sgemm_bias_act_kernel<true><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K, 0.f);
         std::swap(cur, nxt);
       } else {
-        sgemm_bias_act_kernel<false><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K);
+        sgemm_bias_act_kernel<false><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K,
+                                                           want_depth ? -1.f : 0.f);
+        *is_depth = want_depth ? 1 : 0;
       }
       c->launches++;
     }
@@ -504,7 +508,7 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       T.lnl = lnl ? lnl + p0 : nullptr;
       T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
       T.status = c->status;
-      if (c->use_fast && c->allow_fast) {
+      if (c->use_fast && c->allow_fast && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
         switch (T.log2N1) {
           case 10: tail_fast_kernel<10><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;

@@ -59,6 +59,9 @@ struct TailParams {
   double fixed[PAYNE_NPAR];
   int n_poly;
   int poly_col[PAYNE_MAX_POLY];
+  int n_labels;                 // emulator inputs: a row whose labels are all finite cannot hold NaN
+  int label_col[8];
+  double label_fixed[8];
   // batch
   const double* theta;
   long long ld;
@@ -82,14 +85,15 @@ struct PointSetup {
   double poly[PAYNE_MAX_POLY];
   float taper_a;        // exp(-a k^2)
   float hdu;
-  int do_rot, use_inst, bad, i0, i1, log2N2;
+  int do_rot, use_inst, bad, i0, i1, log2N2, clean;
 };
 
 __device__ __forceinline__ double get_par(const TailParams& P, const double* th, int which) {
   return P.col[which] >= 0 ? th[P.col[which]] : P.fixed[which];
 }
 
-__device__ __forceinline__ int zidx(int k) { return 2 * swz(k >> 1) + (k & 1); }
+// float index of real sample k: 2*swz(k>>1) + (k&1) == k ^ (((k>>5)&7)<<2)
+__device__ __forceinline__ int zidx(int k) { return k ^ (((k >> 5) & 7) << 2); }
 
 // largest j in [lo, hi] with w[j]*D <= x, assuming w[lo]*D <= x; starts from a guess.
 __device__ __forceinline__ int locate(const double* __restrict__ w, double D, double x, int guess,
@@ -171,6 +175,11 @@ __device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S)
   const double vrad = get_par(P, th, PAYNE_P_VRAD);
   const double instR = get_par(P, th, PAYNE_P_INSTR);
   S.bad = 0;
+  S.clean = 1;
+  for (int i = 0; i < P.n_labels; ++i) {
+    const double v = P.label_col[i] >= 0 ? th[P.label_col[i]] : P.label_fixed[i];
+    if (!isfinite(v)) S.clean = 0;
+  }
   S.do_rot = (vrot != 0.0);                       // predictspec.py:231 (NaN != 0 is true)
   if (vrot != vrot) S.bad = 1;                    // NaN kernel -> NaN spectrum
   S.vsini_scale = fabs(vrot) * P.sb_scale;        // sigma = sqrt(vsini^2 - 0) (smoothing.py:297)

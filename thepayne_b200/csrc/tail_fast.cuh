@@ -19,7 +19,7 @@ namespace payne {
 
 struct FastGrid {
   // stage 1 forward (native -> 2^k grid) and back: p = k * num / den
-  int f_num, f_den, f_incj, f_incr;   // num = n-1,  den = N1-1, inc = divmod(256*num, den)
+  int f_num, f_den, f_incj, f_incr;   // num = n-1,  den = N1-1, inc = divmod(2*256*num, den) (pairs)
   int b_num, b_den, b_incj, b_incr;   // num = N1-1, den = n-1
   float f_invden, b_invden;
   float c_native;                     // dlnw / 2   (source spacing = native grid)
@@ -31,7 +31,7 @@ struct FastGrid {
 };
 
 struct FastSetup {
-  int s_incj, s_incr, s_den, s_num;   // stage 2: num = nM-1, den = N2-1
+  int s_incj, s_incr, s_den, s_num;   // stage 2: num = nM-1, den = N2-1, inc for pairs (2*256*num)
   float s_invden;
   double q0, scale;                   // final: p = (obs_q - q0) * scale
 };
@@ -45,6 +45,42 @@ __device__ __forceinline__ void divmod_init(int tid, int num, int den, int& j, i
 
 __device__ __forceinline__ float interp_w(float delta, float c) {   // delta (1 + (delta-1) c)
   return fmaf(delta * (delta - 1.f), c, delta);
+}
+
+template <bool CLEAN>
+__device__ __forceinline__ float ld_depth(const float* row, int j) {
+  float v = row[j];
+  if (!CLEAN && v != v) v = 0.f;        // nan_to_num(nan=1.0) (smoothing.py:138) in depth space
+  return v;
+}
+
+// Regrid a line-depth row (global/L2) onto N uniform ln-lambda points in shared memory:
+// out[k] = np.interp at native position j0 + k*num/den (num <= den).  Each thread makes PAIRS of
+// adjacent outputs (three row loads for two outputs, one 8-byte smem store); the source index of
+// the very last output is clamped with min(), its weight is exactly 0 there.
+template <bool CLEAN>
+__device__ __forceinline__ void regrid_in(const float* row, float* zf, int tid, int N, int num, int den,
+                                          int j0, int jlast, float invden, float c, int inc2j, int inc2r) {
+  const long long v = 2LL * tid * num;
+  int j = (int)(v / den);
+  int rem = (int)(v - (long long)j * den);
+  j += j0;
+#pragma unroll 4
+  for (int k = 2 * tid; k < N; k += 2 * kNT) {
+    int rem1 = rem + num, j1 = j;
+    if (rem1 >= den) { rem1 -= den; ++j1; }
+    const float r0 = ld_depth<CLEAN>(row, j);
+    const float r1 = ld_depth<CLEAN>(row, min(j + 1, jlast));
+    const float r2 = ld_depth<CLEAN>(row, min(j + 2, jlast));
+    const bool same = (j1 == j);
+    const float a1 = same ? r0 : r1, b1 = same ? r1 : r2;
+    float2 o;
+    o.x = fmaf(interp_w((float)rem * invden, c), r1 - r0, r0);
+    o.y = fmaf(interp_w((float)rem1 * invden, c), b1 - a1, a1);
+    *reinterpret_cast<float2*>(zf + zidx(k)) = o;
+    j += inc2j; rem += inc2r;
+    if (rem >= den) { rem -= den; ++j; }
+  }
 }
 
 template <int LOG2N1>
@@ -69,7 +105,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       if (!S.bad && S.use_inst) {
         const int nM = S.i1 - S.i0 + 1, N2 = 1 << S.log2N2;
         FS.s_num = nM - 1; FS.s_den = N2 - 1;
-        const long long inc = (long long)kNT * (nM - 1);
+        const long long inc = 2LL * kNT * (nM - 1);
         FS.s_incj = (int)(inc / (N2 - 1));
         FS.s_incr = (int)(inc - (long long)FS.s_incj * (N2 - 1));
         FS.s_invden = 1.0f / (float)(N2 - 1);
@@ -85,24 +121,13 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       __syncthreads();
       continue;
     }
-    bool is_depth = P.flux_is_depth != 0;
+    const bool is_depth = true;   // this kernel is only launched on line-depth rows (f - 1)
 
     // ---------------- stage 1: rotational broadening on the full emulator grid
     if (S.do_rot) {
       const int n = P.n;
-      {
-        int j, rem;
-        divmod_init<int>(tid, F.f_num, F.f_den, j, rem);
-#pragma unroll 4
-        for (int k = tid; k < N1; k += kNT) {
-          int jj = j; float dl = (float)rem * F.f_invden;
-          if (jj >= n - 1) { jj = n - 2; dl = 1.f; }
-          const float a = depth_of(row[jj], is_depth, true), b = depth_of(row[jj + 1], is_depth, true);
-          zf[zidx(k)] = fmaf(interp_w(dl, F.c_native), b - a, a);
-          j += F.f_incj; rem += F.f_incr;
-          if (rem >= F.f_den) { rem -= F.f_den; ++j; }
-        }
-      }
+      if (S.clean) regrid_in<true>(row, zf, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+      else regrid_in<false>(row, zf, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
       __syncthreads();
       RotH H{P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
       ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
@@ -111,9 +136,8 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
         divmod_init<int>(tid, F.b_num, F.b_den, k, rem);
 #pragma unroll 4
         for (int i = tid; i < n; i += kNT) {
-          int kk = k; float dl = (float)rem * F.b_invden;
-          if (kk >= N1 - 1) { kk = N1 - 2; dl = 1.f; }
-          const float g0 = zf[zidx(kk)], g1 = zf[zidx(kk + 1)];
+          const float dl = (float)rem * F.b_invden;
+          const float g0 = zf[zidx(k)], g1 = zf[zidx(min(k + 1, N1 - 1))];
           const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
           if (i > 0 && i < n - 1) {                  // edge patch of predictspec.py:240-241
             row[i] = v;
@@ -124,7 +148,6 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
           if (rem >= F.b_den) { rem -= F.b_den; ++k; }
         }
       }
-      is_depth = true;
       __syncthreads();
     }
 
@@ -133,22 +156,8 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       // ---------------- stage 2: mask, regrid, Gaussian broadening
       const int log2N2 = S.log2N2, N2 = 1 << log2N2;
       const int i0 = S.i0, i1 = S.i1;
-      {
-        int j, rem;
-        divmod_init<int>(tid, FS.s_num, FS.s_den, j, rem);
-        j += i0;
-        const int incj = FS.s_incj, incr = FS.s_incr, den = FS.s_den;
-        const float invden = FS.s_invden;
-#pragma unroll 4
-        for (int k = tid; k < N2; k += kNT) {
-          int jj = j; float dl = (float)rem * invden;
-          if (jj >= i1) { jj = i1 - 1; dl = 1.f; }
-          const float a = depth_of(row[jj], is_depth, true), b = depth_of(row[jj + 1], is_depth, true);
-          zf[zidx(k)] = fmaf(interp_w(dl, F.c_native), b - a, a);
-          j += incj; rem += incr;
-          if (rem >= den) { rem -= den; ++j; }
-        }
-      }
+      if (S.clean) regrid_in<true>(row, zf, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+      else regrid_in<false>(row, zf, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
       __syncthreads();
       GaussH H{S.taper_a, 2.0f / (float)N2};
       if (log2N2 == LOG2N1) {
