@@ -26,6 +26,9 @@ CASES = {
     'mini_edge': (dict(kind='mini', obs_range=(5139.0, 5160.0), n_obs=600), 4, 4),
     'c2': (dict(kind='c2'), 48, 6),
     'c3': (dict(kind='c3'), 16, 2),
+    # 32768-point transforms (one CTA per SM) and 65536-point split transforms (C4-shaped)
+    'mid': (dict(kind='mini', ann_range=(5100.0, 5400.0), obs_range=(5120.0, 5380.0), n_obs=3000), 12, 3),
+    'c4m': (dict(kind='c4'), 8, 2),
 }
 
 
@@ -34,7 +37,7 @@ def build(name, model_fn):
     kind = kw.pop('kind')
     drop = kw.pop('drop', [])
     fixed = kw.pop('fixed', {})
-    base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3}[kind]
+    base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3, 'c4': synth.config_c4}[kind]
     if not drop and not fixed:
         return base(model_fn, **kw)
 

@@ -201,6 +201,82 @@ __device__ __forceinline__ void ct_filter_pairs(float2* z, const TwTab& tw, cons
   __syncthreads();
 }
 
+// Same for the odd-frequency half of a split transform (see ct_convolve_split): local index k'
+// stands for frequency k = 2k'+1 of a transform of size M = 2 Mh, whose partner M-k = 2(Mh-1-k')+1
+// is the bitwise complement of k' -- in digit-reversed storage: row' = Mlo-1-row, c' = 15-c.
+// H(k), k in [0, M], includes 1/M.
+template <int LOG2MH, class HF>
+__device__ __forceinline__ void ct_filter_pairs_odd(float2* z, const TwTab& tw, const HF& H, int tid) {
+  using P = CtPlan<LOG2MH>;
+  constexpr int Mh = 1 << LOG2MH, Mlo = Mh >> 4, M = 2 * Mh;
+  constexpr int NITEMS = (Mlo >> 1) << 4;
+  const int c = tid & 15;
+#pragma unroll 2
+  for (int w = tid; w < NITEMS; w += kNT) {
+    const int klo = w >> 4;
+    const int row = P::row_of(klo);
+    const int kp = klo + (c << (LOG2MH - 4));
+    const int k = 2 * kp + 1;
+    const int pk = swz((row << 4) + c);
+    const int pp = swz(((Mlo - 1 - row) << 4) + (15 - c));
+    const float2 Zk = z[pk], Zp = z[pp];
+    const float2 W = tw_load<LOG2MH + 2>(tw, k);          // exp(-2 pi i k / N), N = 2M = 4 Mh
+    const float hk = H(k), hm = H(M - k);
+    const float A = 0.5f * (hk + hm), Bc = 0.5f * (hk - hm);
+    const float2 E = make_float2(0.5f * (Zk.x + Zp.x), 0.5f * (Zk.y - Zp.y));
+    const float2 O = make_float2(0.5f * (Zk.y + Zp.y), -0.5f * (Zk.x - Zp.x));
+    const float2 WO = cmul(W, O), WcE = cmulc(E, W);
+    const float2 E2 = make_float2(A * E.x + Bc * WO.x, A * E.y + Bc * WO.y);
+    const float2 O2 = make_float2(Bc * WcE.x + A * O.x, Bc * WcE.y + A * O.y);
+    z[pk] = make_float2(E2.x - O2.y, E2.y + O2.x);
+    z[pp] = make_float2(E2.x + O2.y, O2.x - E2.y);
+  }
+  __syncthreads();
+}
+
+template <class HF>
+struct EvenBins {      // H restricted to even frequencies: local k' -> H(2k')
+  const HF& H;
+  __device__ __forceinline__ float operator()(int k) const { return H(2 * k); }
+};
+
+// Convolution of a real signal of N = 4 Mh samples that does not fit one SM's shared memory:
+// complex points [0, Mh) live in shared memory (swizzled), points [Mh, 2Mh) in a global scratch
+// line `g` that stays in L2.  One radix-2 DIF step across the halves leaves the even frequencies
+// in the first half and the odd ones in the second; the pairs (k, M-k) of the filter stage never
+// mix the two classes, so each half is transformed, filtered and transformed back entirely in
+// shared memory (the halves swap places once), and a radix-2 DIT step restores natural order.
+template <int LOG2MH, class HF>
+__device__ __forceinline__ void ct_convolve_split(float2* z, float2* g, const TwTab& tw, const TwConst& tc,
+                                                  const HF& H, int tid) {
+  constexpr int Mh = 1 << LOG2MH;
+  for (int j = tid; j < Mh; j += kNT) {                  // cross DIF
+    const float2 a = z[swz(j)], b = g[j];
+    z[swz(j)] = a + b;
+    g[j] = cmul(a - b, tw_load<LOG2MH + 1>(tw, j));      // W_M^j, M = 2 Mh
+  }
+  __syncthreads();
+  ct_fft_forward<LOG2MH>(z, tw, tc, tid);
+  ct_filter_pairs<LOG2MH>(z, tw, EvenBins<HF>{H}, tid);
+  ct_fft_inverse<LOG2MH>(z, tw, tc, tid);
+  for (int j = tid; j < Mh; j += kNT) {                  // swap halves
+    const float2 a = z[swz(j)];
+    z[swz(j)] = g[j];
+    g[j] = a;
+  }
+  __syncthreads();
+  ct_fft_forward<LOG2MH>(z, tw, tc, tid);
+  ct_filter_pairs_odd<LOG2MH>(z, tw, H, tid);
+  ct_fft_inverse<LOG2MH>(z, tw, tc, tid);
+  for (int j = tid; j < Mh; j += kNT) {                  // cross DIT
+    const float2 a = g[j];
+    const float2 b = cmulc(z[swz(j)], tw_load<LOG2MH + 1>(tw, j));
+    z[swz(j)] = a + b;
+    g[j] = a - b;
+  }
+  __syncthreads();
+}
+
 template <int LOG2M, class HF>
 __device__ __forceinline__ void ct_convolve(float2* z, const TwTab& tw, const TwConst& tc, const HF& H, int tid) {
   ct_fft_forward<LOG2M>(z, tw, tc, tid);

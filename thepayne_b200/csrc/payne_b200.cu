@@ -261,9 +261,10 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   float2* dtw;
   rc = upload_owned(c, &dtw, tw.data(), tw.size()); if (rc) return rc;
   T.tw = dtw; T.log2tw = l2; T.max_log2N = l2;
-  c->tail_smem = (size_t)4 * N1;
-  if (c->tail_smem > 227 * 1024 - 2048)
-    return fail(PAYNE_E_UNSUPPORTED, "emulator grid needs an FFT larger than one SM's shared memory");
+  // one 8-byte slot per complex point; from 65536 samples on only half of them sit in shared
+  // memory (split transform, fast tail only)
+  c->tail_smem = l2 >= 16 ? (size_t)2 * N1 : (size_t)4 * N1;
+  if (l2 > 16) return fail(PAYNE_E_UNSUPPORTED, "emulator grids above 65536 pixels are not supported");
 
   // ---- observation
   const int no = obs->n_obs;
@@ -324,7 +325,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
       float te; std::memcpy(&te, &back[i].y, 4);
       worst = std::max(worst, std::fabs(((double)k + ta) - ((double)back[i].x + (double)te)));
     }
-    c->use_fast = (worst < 2e-7) && l2 >= 10 && l2 <= 15;
+    c->use_fast = (worst < 2e-7) && l2 >= 10 && l2 <= 16;
     std::vector<double> oq(no), oot(no);
     for (int j = 0; j < no; ++j) {
       oq[j] = (lnw[j] - T.lnw0) * F.inv_dlnw;
@@ -353,20 +354,31 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
       break;
     switch (l2) {
       PAYNE_FAST_CASE(10) PAYNE_FAST_CASE(11) PAYNE_FAST_CASE(12) PAYNE_FAST_CASE(13)
-      PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15)
+      PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15) PAYNE_FAST_CASE(16)
       default: break;
     }
 #undef PAYNE_FAST_CASE
     if (e1 != cudaSuccess || e2 != cudaSuccess || occf < 1) c->use_fast = 0;
     c->tail_grid_fast = occf * c->sm_count;
+    if (c->use_fast && l2 >= 16) {
+      float* sc = nullptr;
+      CU_TRY(cudaMalloc((void**)&sc, (size_t)c->tail_grid_fast * (N1 / 2) * sizeof(float)));
+      c->owned.push_back(sc);
+      c->fast.scratch = sc;
+    }
   }
-  CU_TRY(cudaFuncSetAttribute(payne::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)c->tail_smem));
-  int occ = 0;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_kernel, payne::kTailThreads,
-                                                       c->tail_smem));
-  if (occ < 1) return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
-  c->tail_grid = occ * c->sm_count;
+  if (l2 <= 15) {
+    CU_TRY(cudaFuncSetAttribute(payne::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)c->tail_smem));
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_kernel, payne::kTailThreads,
+                                                         c->tail_smem));
+    if (occ < 1) return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
+    c->tail_grid = occ * c->sm_count;
+  } else if (!c->use_fast) {
+    return fail(PAYNE_E_UNSUPPORTED,
+                "a 65536-point transform needs the log-uniform fast tail (emulator grid is not log-uniform)");
+  }
   // tensor-core operand copies of the weights
   for (int k = 1; k < 6; ++k) {
     rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
@@ -516,9 +528,11 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
           case 12: tail_fast_kernel<12><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
           case 13: tail_fast_kernel<13><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
           case 14: tail_fast_kernel<14><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          default: tail_fast_kernel<15><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 15: tail_fast_kernel<15><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          default: tail_fast_kernel<16><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
         }
       } else {
+        if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
         tail_kernel<<<std::min(c->tail_grid, nb), kTailThreads, c->tail_smem, st>>>(T);
       }
       c->launches++;

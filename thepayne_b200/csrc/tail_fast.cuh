@@ -27,6 +27,7 @@ struct FastGrid {
   double dlnw, inv_dlnw;
   const double* obs_q;                // [n_obs] (ln lambda_j - ln w_0) / dlnw
   const double* obs_otm1;             // [n_obs] (flux - 1)/eflux : r = depth/eflux - otm1
+  float* scratch;                     // [grid, N1/2] second half of split transforms (N1 = 65536)
   TwConst twc;
 };
 
@@ -54,12 +55,29 @@ __device__ __forceinline__ float ld_depth(const float* row, int j) {
   return v;
 }
 
+// Where the N real samples of the current transform live.
+struct ZSmem {                       // all in shared memory (N <= 32768)
+  float* zf;
+  __device__ __forceinline__ float ld(int k) const { return zf[zidx(k)]; }
+  __device__ __forceinline__ void st2(int k, float2 v) const { *reinterpret_cast<float2*>(zf + zidx(k)) = v; }
+};
+struct ZSplit {                      // first half in shared memory, second half in an L2-resident scratch line
+  float* zf;
+  float* g;
+  int half;
+  __device__ __forceinline__ float ld(int k) const { return k < half ? zf[zidx(k)] : __ldcg(g + (k - half)); }
+  __device__ __forceinline__ void st2(int k, float2 v) const {
+    if (k < half) *reinterpret_cast<float2*>(zf + zidx(k)) = v;
+    else *reinterpret_cast<float2*>(g + (k - half)) = v;
+  }
+};
+
 // Regrid a line-depth row (global/L2) onto N uniform ln-lambda points in shared memory:
 // out[k] = np.interp at native position j0 + k*num/den (num <= den).  Each thread makes PAIRS of
 // adjacent outputs (three row loads for two outputs, one 8-byte smem store); the source index of
 // the very last output is clamped with min(), its weight is exactly 0 there.
-template <bool CLEAN>
-__device__ __forceinline__ void regrid_in(const float* row, float* zf, int tid, int N, int num, int den,
+template <bool CLEAN, class ZV>
+__device__ __forceinline__ void regrid_in(const float* row, const ZV& zv, int tid, int N, int num, int den,
                                           int j0, int jlast, float invden, float c, int inc2j, int inc2r) {
   const long long v = 2LL * tid * num;
   int j = (int)(v / den);
@@ -77,12 +95,87 @@ __device__ __forceinline__ void regrid_in(const float* row, float* zf, int tid, 
     float2 o;
     o.x = fmaf(interp_w((float)rem * invden, c), r1 - r0, r0);
     o.y = fmaf(interp_w((float)rem1 * invden, c), b1 - a1, a1);
-    *reinterpret_cast<float2*>(zf + zidx(k)) = o;
+    zv.st2(k, o);
     j += inc2j; rem += inc2r;
     if (rem >= den) { rem -= den; ++j; }
   }
 }
 
+// ---- per-stage building blocks, templated on the sample view -------------------------------
+template <class ZV>
+__device__ __forceinline__ void stage_regrid(const PointSetup& S, const float* row, const ZV& zv, int tid, int N,
+                                             int num, int den, int j0, int jlast, float invden, float c,
+                                             int incj, int incr) {
+  if (S.clean) regrid_in<true>(row, zv, tid, N, num, den, j0, jlast, invden, c, incj, incr);
+  else regrid_in<false>(row, zv, tid, N, num, den, j0, jlast, invden, c, incj, incr);
+}
+
+// stage-1 output back onto the emulator grid (+ edge patch of predictspec.py:240-241)
+template <class ZV>
+__device__ __forceinline__ void regrid_back(float* row, const ZV& zv, const FastGrid& F, int tid, int n, int N1) {
+  int k, rem;
+  divmod_init<int>(tid, F.b_num, F.b_den, k, rem);
+#pragma unroll 4
+  for (int i = tid; i < n; i += kNT) {
+    const float dl = (float)rem * F.b_invden;
+    const float g0 = zv.ld(k), g1 = zv.ld(min(k + 1, N1 - 1));
+    const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
+    if (i > 0 && i < n - 1) {
+      row[i] = v;
+      if (i == 1) row[0] = v;
+      if (i == n - 2) row[n - 1] = v;
+    }
+    k += F.b_incj; rem += F.b_incr;
+    if (rem >= F.b_den) { rem -= F.b_den; ++k; }
+  }
+}
+
+// observed pixels, continuum, residuals; returns this thread's partial chi2
+template <class ZV>
+__device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid& F, const PointSetup& S,
+                                             const FastSetup& FS, const ZV& zv, int tid, int p, int N2) {
+  const double nan = CUDART_NAN;
+  const double pmax = (double)(N2 - 1);
+  const float hdu = S.hdu;
+  const double q0 = FS.q0, scale = FS.scale;
+  double acc = 0.0;
+  if (P.n_poly == 0 && P.model_out == nullptr) {
+#pragma unroll 4
+    for (int j = tid; j < P.n_obs; j += kNT) {
+      const double pp = (__ldg(F.obs_q + j) - q0) * scale;
+      double r;
+      if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
+      else {
+        const int k = min((int)pp, N2 - 2);
+        const float dl = (float)(pp - (double)k);
+        const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
+        const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
+        r = fma((double)d, __ldg(P.obs_inv_s + j), -__ldg(F.obs_otm1 + j));
+      }
+      acc = fma(r, r, acc);
+    }
+  } else {
+    for (int j = tid; j < P.n_obs; j += kNT) {
+      const double pp = (__ldg(F.obs_q + j) - q0) * scale;
+      double m;
+      if (!(pp >= 0.0 && pp <= pmax)) m = nan;
+      else {
+        const int k = min((int)pp, N2 - 2);
+        const float dl = (float)(pp - (double)k);
+        const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
+        m = 1.0 + (double)fmaf(interp_w(dl, hdu), g1 - g0, g0);
+      }
+      if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
+      if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
+      const double r = m * __ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
+      acc += r * r;
+    }
+  }
+  return acc;
+}
+
+// LOG2N1 <= 15: the whole transform sits in shared memory (3 CTAs/SM up to 2^14).
+// LOG2N1 == 16: split transform, half in shared memory (128 KB), half in the scratch line.
 template <int LOG2N1>
 __global__ void __launch_bounds__(kNT, LOG2N1 <= 14 ? 3 : 1)
 tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
@@ -96,6 +189,11 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   const TwTab tw{P.tw, P.log2tw};
   const double nan = CUDART_NAN;
   constexpr int N1 = 1 << LOG2N1;
+  constexpr bool kSplit = LOG2N1 >= 16;
+  constexpr int LOG2MH = kSplit ? LOG2N1 - 2 : 8;          // complex points per half (split only)
+  float* gline = kSplit ? F.scratch + (size_t)blockIdx.x * (N1 / 2) : nullptr;
+  const ZSmem zs{zf};
+  const ZSplit zp{zf, gline, N1 / 2};
 
   for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
     const double* th = P.theta + (long long)p * P.ld;
@@ -126,27 +224,17 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     // ---------------- stage 1: rotational broadening on the full emulator grid
     if (S.do_rot) {
       const int n = P.n;
-      if (S.clean) regrid_in<true>(row, zf, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
-      else regrid_in<false>(row, zf, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
-      __syncthreads();
       RotH H{P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
-      ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
-      {
-        int k, rem;
-        divmod_init<int>(tid, F.b_num, F.b_den, k, rem);
-#pragma unroll 4
-        for (int i = tid; i < n; i += kNT) {
-          const float dl = (float)rem * F.b_invden;
-          const float g0 = zf[zidx(k)], g1 = zf[zidx(min(k + 1, N1 - 1))];
-          const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
-          if (i > 0 && i < n - 1) {                  // edge patch of predictspec.py:240-241
-            row[i] = v;
-            if (i == 1) row[0] = v;
-            if (i == n - 2) row[n - 1] = v;
-          }
-          k += F.b_incj; rem += F.b_incr;
-          if (rem >= F.b_den) { rem -= F.b_den; ++k; }
-        }
+      if constexpr (!kSplit) {
+        stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+        __syncthreads();
+        ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
+        regrid_back(row, zs, F, tid, n, N1);
+      } else {
+        stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+        __syncthreads();
+        ct_convolve_split<LOG2MH>(z, reinterpret_cast<float2*>(gline), tw, F.twc, H, tid);
+        regrid_back(row, zp, F, tid, n, N1);
       }
       __syncthreads();
     }
@@ -156,56 +244,32 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       // ---------------- stage 2: mask, regrid, Gaussian broadening
       const int log2N2 = S.log2N2, N2 = 1 << log2N2;
       const int i0 = S.i0, i1 = S.i1;
-      if (S.clean) regrid_in<true>(row, zf, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
-      else regrid_in<false>(row, zf, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
-      __syncthreads();
       GaussH H{S.taper_a, 2.0f / (float)N2};
-      if (log2N2 == LOG2N1) {
-        ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
-      } else if (LOG2N1 >= 10 && log2N2 == LOG2N1 - 1) {
-        ct_convolve<(LOG2N1 >= 10 ? LOG2N1 - 2 : 8)>(z, tw, F.twc, H, tid);
-      } else {
-        const Twiddles twr{P.tw, P.log2tw};
-        FftPlan plan; plan.make(log2N2 - 1);
-        fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
-        filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
-        fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
-      }
-      // ---------------- onto the observed pixels, continuum, chi2
-      const double pmax = (double)(N2 - 1);
-      const float hdu = S.hdu;
-      const double q0 = FS.q0, scale = FS.scale;
-      if (P.n_poly == 0 && P.model_out == nullptr) {
-#pragma unroll 4
-        for (int j = tid; j < P.n_obs; j += kNT) {
-          const double pp = (__ldg(F.obs_q + j) - q0) * scale;
-          double r;
-          if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
-          else {
-            const int k = min((int)pp, N2 - 2);
-            const float dl = (float)(pp - (double)k);
-            const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
-            const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
-            r = fma((double)d, __ldg(P.obs_inv_s + j), -__ldg(F.obs_otm1 + j));
-          }
-          acc = fma(r, r, acc);
+      bool split2 = false;
+      if constexpr (kSplit) split2 = (log2N2 == LOG2N1);
+      if (split2) {
+        if constexpr (kSplit) {
+          stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+          __syncthreads();
+          ct_convolve_split<LOG2MH>(z, reinterpret_cast<float2*>(gline), tw, F.twc, H, tid);
+          acc = final_pass(P, F, S, FS, zp, tid, p, N2);
         }
       } else {
-        for (int j = tid; j < P.n_obs; j += kNT) {
-          const double pp = (__ldg(F.obs_q + j) - q0) * scale;
-          double m;
-          if (!(pp >= 0.0 && pp <= pmax)) m = nan;
-          else {
-            const int k = min((int)pp, N2 - 2);
-            const float dl = (float)(pp - (double)k);
-            const float g0 = zf[zidx(k)], g1 = zf[zidx(k + 1)];
-            m = 1.0 + (double)fmaf(interp_w(dl, hdu), g1 - g0, g0);
-          }
-          if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
-          if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
-          const double r = m * __ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
-          acc += r * r;
+        stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+        __syncthreads();
+        constexpr int LA = kSplit ? 15 : LOG2N1;            // largest all-in-smem transform here
+        if (log2N2 == LA) {
+          ct_convolve<LA - 1>(z, tw, F.twc, H, tid);
+        } else if (LA >= 10 && log2N2 == LA - 1) {
+          ct_convolve<(LA >= 10 ? LA - 2 : 8)>(z, tw, F.twc, H, tid);
+        } else {
+          const Twiddles twr{P.tw, P.log2tw};
+          FftPlan plan; plan.make(log2N2 - 1);
+          fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
+          filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
+          fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
         }
+        acc = final_pass(P, F, S, FS, zs, tid, p, N2);
       }
     } else {
       // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289)

@@ -242,6 +242,15 @@ def config_c3(model_fn, **kw):
     return build_config('C3-joint', model_fn=model_fn, bands=PROCYON_BANDS, **kw)
 
 
+def config_c4(model_fn, **kw):
+    """C4 (monolithic variant): full-wavelength emulator LinNet 5-512-512-512-51784 (vmic label),
+    65536-point transforms, n_obs 25000, order-4 continuum, Vrot up to 100 km/s."""
+    args = dict(ann_range=(4750.0, 5500.0), obs_range=(4760.0, 5490.0), n_obs=25000, H=512, vmic=True,
+                npoly=5, vrot_max=100.0)
+    args.update(kw)
+    return build_config('C4-full', model_fn=model_fn, **args)
+
+
 def config_mini(model_fn, **kw):
     """Small everything: fast on the CPU oracle; used for golden vectors."""
     args = dict(ann_range=(5140.0, 5190.0), obs_range=(5150.0, 5180.0), n_obs=1500, H=64)

@@ -126,3 +126,56 @@ if __name__ == '__main__':
         kk = np.arange(M)
         e1 = np.abs(Zd[freq_to_pos(kk, plan, M)] - np.fft.fft(z)).max()
         print(N, plan, 'fft err', e1, 'conv err', np.abs(ref - got).max())
+
+
+def filter_pairs_odd(x, H, plan):
+    """Odd-frequency half of a split transform: local k' <-> frequency 2k'+1 of size M = 2*len(x);
+    partner is the complement Mh-1-k'.  Mirrors ct_filter_pairs_odd in csrc/fft_ct.cuh."""
+    Mh = len(x)
+    M, N = 2 * Mh, 4 * Mh
+    kp = np.arange(Mh // 2)
+    # enumerate like the kernel: klo in [0, Mlo/2), c in [0,16)
+    Mlo = Mh >> 4
+    klo, c = np.meshgrid(np.arange(Mlo // 2), np.arange(16), indexing='ij')
+    klo, c = klo.ravel(), c.ravel()
+    kloc = klo + c * Mlo
+    rows = freq_to_pos(klo, plan[:-1], Mlo)
+    pk = rows * 16 + c
+    pp = (Mlo - 1 - rows) * 16 + (15 - c)
+    assert np.array_equal(pp, freq_to_pos(Mh - 1 - kloc, plan, Mh))
+    k = 2 * kloc + 1
+    Zk, Zp = x[pk], x[pp]
+    E = 0.5 * (Zk + np.conj(Zp))
+    O = -0.5j * (Zk - np.conj(Zp))
+    W = np.exp(-2j * np.pi * k / N)
+    A = 0.5 * (H[k] + H[M - k])
+    Bc = 0.5 * (H[k] - H[M - k])
+    E2 = A * E + Bc * W * O
+    O2 = Bc * np.conj(W) * E + A * O
+    out = x.copy()
+    out[pk] = E2 + 1j * O2
+    out[pp] = np.conj(E2) + 1j * np.conj(O2)
+    return out
+
+
+def conv_real_split(sig, H):
+    """csrc/fft_ct.cuh::ct_convolve_split: N = 4*Mh real samples, two halves of Mh complex points."""
+    N = len(sig)
+    M = N // 2
+    Mh = M // 2
+    plan = radix_plan(int(np.log2(Mh)))
+    zz = sig[0::2] + 1j * sig[1::2]
+    a, b = zz[:Mh].copy(), zz[Mh:].copy()
+    j = np.arange(Mh)
+    WM = np.exp(-2j * np.pi * j / M)
+    a, b = a + b, (a - b) * WM                       # cross DIF
+    Hs = H / M
+    a = dit_inverse(filter_pairs(dif_forward(a, plan), Hs[0::2] * Mh, plan), plan) * Mh   # undo model's 1/Mh
+    b = dit_inverse(filter_pairs_odd(dif_forward(b, plan), Hs * Mh, plan), plan) * Mh
+    a = a / Mh
+    b = b / Mh
+    b = b * np.conj(WM)                              # cross DIT
+    out_z = np.concatenate([a + b, a - b])
+    out = np.empty(N)
+    out[0::2], out[1::2] = out_z.real, out_z.imag
+    return out
