@@ -38,5 +38,20 @@ def main(names):
               'nan', int(np.isnan(lnl).sum()))
 
 
+def prior_golden():
+    """Unit-cube samples -> reference prior.priortrans / lnpriorfn (Payne/fitting/prior.py)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    from test_batching import FREE, NAMES, PRIORS
+    U = np.random.default_rng(0).random((64, len(FREE)))
+    U[0, :] = 1.0 - 1e-16
+    theta, lnp = refharness.ref_prior(PRIORS, NAMES, FREE, [True, True, True, True, False], U)
+    np.savez_compressed(os.path.join(OUT, 'prior.npz'), U=U, theta=theta, lnp=lnp)
+    print('prior', theta.shape, 'finite', int(np.isfinite(theta).all()), 'lnp[:3]', lnp[:3])
+
+
 if __name__ == '__main__':
-    main(sys.argv[1:] or list(goldens.CASES))
+    names = sys.argv[1:] or (list(goldens.CASES) + ['prior'])
+    if 'prior' in names:
+        names.remove('prior')
+        prior_golden()
+    main(names)

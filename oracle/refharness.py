@@ -49,6 +49,16 @@ def load():
     for name in ['h5py', 'dynesty', 'astropy', 'astropy.io']:
         if name not in sys.modules:
             sys.modules[name] = types.ModuleType(name)
+    # advancedpriors.py:14-25 imports a few astropy names at module level; none is used by the
+    # pv_* transforms or the additive gaussian/uniform priors exercised here
+    for name in ['astropy.utils', 'astropy.utils.exceptions', 'astropy.units', 'astropy.coordinates']:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['astropy.utils.exceptions'].AstropyWarning = type('AstropyWarning', (Warning,), {})
+    sys.modules['astropy.utils.exceptions'].AstropyDeprecationWarning = type('AstropyDeprecationWarning', (Warning,), {})
+    sys.modules['astropy'].units = sys.modules['astropy.units']
+    sys.modules['astropy.coordinates'].SkyCoord = object
+    sys.modules['astropy.coordinates'].CylindricalRepresentation = object
     asc = types.ModuleType('astropy.io.ascii')
     asc.read = _ascii_read
     sys.modules['astropy.io.ascii'] = asc
@@ -68,7 +78,7 @@ def load():
                         ('predictspec', 'Payne.predict.predictspec'), ('photANN', 'Payne.predict.photANN'),
                         ('highred', 'Payne.predict.highred'), ('predictsed', 'Payne.predict.predictsed'),
                         ('fitutils', 'Payne.fitting.fitutils'), ('genmod', 'Payne.fitting.genmod'),
-                        ('likelihood', 'Payne.fitting.likelihood')]:
+                        ('likelihood', 'Payne.fitting.likelihood'), ('prior', 'Payne.fitting.prior')]:
         setattr(ns, short, importlib.import_module(full))
     _mods = ns
     return ns
@@ -158,6 +168,16 @@ def ref_model_fn(cfg, theta):
     out = ref_model(cfg, theta)
     cfg.obs_flux, cfg.obs_eflux, cfg.obs_phot = tmp
     return out
+
+
+def ref_prior(inpriordict, names, free, runbools, U, fixed=None):
+    """Reference prior.priortrans / lnpriorfn for each row of the unit-cube sample U."""
+    R = load()
+    flags = {n: n in free for n in names}
+    P = R.prior.prior({'fixedpars': dict(fixed or {})}, inpriordict, [names, flags], runbools)
+    theta = np.array([P.priortrans(list(u)) for u in U], dtype=np.float64)
+    lnp = np.array([P.lnpriorfn({k: v for k, v in zip(P.fitpars_i, t)}) for t in theta])
+    return theta, lnp
 
 
 def ref_lnlike(cfg, theta):
