@@ -29,6 +29,8 @@ CASES = {
     # 32768-point transforms (one CTA per SM) and 65536-point split transforms (C4-shaped)
     'mid': (dict(kind='mini', ann_range=(5100.0, 5400.0), obs_range=(5120.0, 5380.0), n_obs=3000), 12, 3),
     'c4m': (dict(kind='c4'), 8, 2),
+    # awkward shapes: hidden width 100 (not a multiple of 8), odd pixel counts
+    'mini_odd': (dict(kind='mini', H=100, ann_range=(5141.0, 5187.3), obs_range=(5150.0, 5180.0), n_obs=1501), 8, 8),
 }
 
 

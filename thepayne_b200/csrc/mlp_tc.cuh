@@ -46,7 +46,7 @@ struct TcWeights {
   void* plane[3] = {nullptr, nullptr, nullptr};   // T: fp32 hi, lo ; X3: bf16 q1, q2, q3
   void* xplane[3] = {nullptr, nullptr, nullptr};
   float* scale = nullptr;                          // X3: per-row power of two
-  int N = 0, K = 0;
+  int N = 0, K = 0, Kp = 0;                        // Kp: row pitch in elements (16-byte multiple for TMA)
 };
 struct TcActs {
   void* plane[3] = {nullptr, nullptr, nullptr};    // sized for fp32; bf16 planes alias the storage
@@ -420,9 +420,9 @@ inline int make_tmap(CUtensorMap* m, const void* ptr, long long rows, int K, lon
 
 // Host-side split of a weight matrix (done once per context).
 inline int tc_prepare_weights(TcWeights* w, const float* W_host, int N, int K, std::vector<void*>* owned) {
-  w->N = N; w->K = K;
-  if (K % 8 != 0) return PAYNE_OK;   // not TMA-addressable; tc_run_layers refuses this layer
-  const size_t n = (size_t)N * K;
+  const int Kp = (K + 7) / 8 * 8;    // TMA needs 16-byte row pitches; the map's extent stays K (OOB = 0)
+  w->N = N; w->K = K; w->Kp = Kp;
+  const size_t n = (size_t)N * Kp;
   std::vector<float> hi(n), lo(n), sc(N);
   std::vector<uint16_t> q[3] = {std::vector<uint16_t>(n), std::vector<uint16_t>(n), std::vector<uint16_t>(n)};
   auto tf32 = [](float x) {   // cvt.rna.tf32: round to nearest, ties away, 10-bit mantissa
@@ -440,8 +440,8 @@ inline int tc_prepare_weights(TcWeights* w, const float* W_host, int N, int K, s
     if (mx > 0.f && std::isfinite(mx)) { std::frexp(mx, &e); s = std::ldexp(1.f, e); }
     sc[r] = s;
     for (int k = 0; k < K; ++k) {
-      const size_t i = (size_t)r * K + k;
-      const float x = W_host[i];
+      const size_t i = (size_t)r * Kp + k;
+      const float x = W_host[(size_t)r * K + k];
       hi[i] = tf32(x); lo[i] = tf32(x - hi[i]);
       const float u = x / s;                                            // exact (power of two)
       const float a1 = std::nearbyint(u * 128.f) / 128.f;
@@ -484,7 +484,7 @@ inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bi
   for (int p = 0; p < Cfg::kPlanes; ++p) {
     const void* wp = MODE == kModeX3 ? W.xplane[p] : W.plane[p];
     if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, Cfg::kElemBytes)) return PAYNE_E_CUDA;
-    if (make_tmap(&T.b[p], wp, W.N, K, K, BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
   }
   for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
   static bool attr_set = false;

@@ -712,7 +712,6 @@ int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_
   TcActs a;
   const long long rows = (M + 127) / 128 * 128, ld = (K + 7) / 8 * 8;
   float *dA = nullptr, *dC = nullptr, *db = nullptr;
-  if (!rc && !w.plane[0]) rc = fail(PAYNE_E_UNSUPPORTED, "K must be a multiple of 8");
   if (!rc) rc = tc_alloc_acts(&a, rows, ld);
   if (!rc && (cudaMalloc((void**)&dA, (size_t)M * K * 4) != cudaSuccess ||
               cudaMalloc((void**)&dC, (size_t)M * N * 4) != cudaSuccess ||
