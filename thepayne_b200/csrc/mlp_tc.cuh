@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/payne_b200.h"
@@ -79,6 +80,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// Same, delivered to the same CTA-relative offset (data and mbarrier signal) of every CTA in mask.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -191,11 +213,15 @@ struct TcGemmArgs {
   int M, N, K;
 };
 
-template <int BN, int MODE, int EPI>
+// MC = 1: the CTAs of a 2-CTA cluster work on the SAME weight tile for two different row tiles;
+// each loads half of the weight rows and TMA-multicasts them to both, so the weight operand
+// crosses L2->SMEM once per pair (the GEMM is bound by that traffic: K is only 256..512).
+template <int BN, int MODE, int EPI, int MC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
   using Cfg = TcCfg<BN, MODE>;
   constexpr int NS = Cfg::kStages, NP = Cfg::kPlanes;
+  const uint32_t crank = MC ? ptx::cluster_ctarank() : 0u;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* stages = base;
@@ -208,21 +234,26 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * NS + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (G.M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
+  const int num_m_true = (G.M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
+  // with MC the two CTAs of a cluster walk pair-tiles in lockstep: row tile 2*mp + crank
+  const int num_m = MC ? (num_m_true + 1) / 2 : num_m_true;
   const int num_tiles = num_m * num_n;
   const int num_kb = (G.K + Cfg::kBK - 1) / Cfg::kBK;
+  const int tile0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < NP; ++p) { ptx::prefetch_tmap(&T.a[p]); ptx::prefetch_tmap(&T.b[p]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], MC ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_ptr, Cfg::kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC) ptx::cluster_sync_all();          // the peer's barriers must exist before anything is multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -230,17 +261,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
     // ===================== TMA producer: stage = [A planes][B planes]
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_wait(&empty[s], ph ^ 1);     // MC: both CTAs' MMAs have released this slot
           unsigned char* st = stages + s * Cfg::kStageBytes;
           ptx::mbar_expect_tx(&full[s], Cfg::kStageBytes);
           const int k0 = kb * Cfg::kBK;
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
             ptx::tma_load_2d(&T.a[p], &full[s], st + p * Cfg::kABytes, k0, m0);
-            ptx::tma_load_2d(&T.b[p], &full[s], st + NP * Cfg::kABytes + p * Cfg::kBBytes, k0, n0);
+            unsigned char* bdst = st + NP * Cfg::kABytes + p * Cfg::kBBytes;
+            if (MC) ptx::tma_load_2d_mc(&T.b[p], &full[s], bdst + crank * (Cfg::kBBytes / 2), k0,
+                                        n0 + (int)crank * (BN / 2), (uint16_t)3);
+            else ptx::tma_load_2d(&T.b[p], &full[s], bdst, k0, n0);
           }
           if (++s == NS) { s = 0; ph ^= 1; }
         }
@@ -252,7 +286,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
       constexpr uint32_t idesc = umma_idesc(BN, MODE == kModeX3 ? 1u : 2u);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         ptx::mbar_wait(&tempty[acc], aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
@@ -286,7 +320,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
               ptx::mma_tf32(d_main, da[0] + ko, db[0] + ko, idesc, first);
             }
           }
-          ptx::mma_commit(&empty[s]);                  // frees the ring slot when the MMAs retire
+          if (MC) ptx::mma_commit_mc(&empty[s], (uint16_t)3);   // release the slot in BOTH CTAs
+          else ptx::mma_commit(&empty[s]);             // frees the ring slot when the MMAs retire
           if (kb == num_kb - 1) ptx::mma_commit(&tfull[acc]);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
@@ -298,8 +333,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
     const int q = warp & 3;
     float* pt = patch + q * (32 * 33);
     int acc = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+      const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
       const int row_base = m0 + q * 32;
@@ -360,6 +395,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC) ptx::cluster_sync_all();          // no multicast / remote commit may target a CTA that has left
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
@@ -475,29 +511,61 @@ inline void tc_free_acts(TcActs* a) {
   a->rows = 0;
 }
 
-template <int BN, int MODE, int EPI>
-inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
-                     void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+// PAYNE_GEMM_MULTICAST=1 enables the 2-CTA weight multicast for the lin6 GEMM.  Measured on B200
+// (C2, B=4096): 0.330 ms vs 0.334 ms without -- no gain, because the bound is each SM's inbound
+// operand bandwidth (96 KB per 1536 MMA-cycles) and the 2-deep ring, neither of which multicast
+// changes; it only removes L2 reads.  Kept (tested) as the stepping stone to cta_group::2 tiles.
+inline bool tc_multicast_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PAYNE_GEMM_MULTICAST"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
+template <int BN, int MODE, int EPI, int MC>
+inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
+                          void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE>;
   static_assert(Cfg::kStages >= 2, "ring too shallow");
   TcMaps T;
   for (int p = 0; p < Cfg::kPlanes; ++p) {
     const void* wp = MODE == kModeX3 ? W.xplane[p] : W.plane[p];
     if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, Cfg::kElemBytes)) return PAYNE_E_CUDA;
-    if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, MC ? BN / 2 : BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
   }
   for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmem) != cudaSuccess) return PAYNE_E_CUDA;
     attr_set = true;
   }
   TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K};
-  const int tiles = ((M + kBM - 1) / kBM) * ((W.N + BN - 1) / BN);
-  const int grid = tiles < sm_count ? tiles : sm_count;
-  tc_gemm_kernel<BN, MODE, EPI><<<grid, kTcThreads, Cfg::kSmem, st>>>(T, G);
+  const int num_m = (M + kBM - 1) / kBM, num_n = (W.N + BN - 1) / BN;
+  if (MC) {
+    const int pair_tiles = ((num_m + 1) / 2) * num_n;
+    int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, EPI, MC>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
+  } else {
+    const int tiles = num_m * num_n;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    tc_gemm_kernel<BN, MODE, EPI, MC><<<grid, kTcThreads, Cfg::kSmem, st>>>(T, G);
+  }
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
+}
+
+template <int BN, int MODE, int EPI>
+inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
+                     void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+  // multicast pays when many row tiles share each weight tile (the wide last layer)
+  if (EPI == 0 && BN >= 128 && M > kBM && tc_multicast_enabled())
+    return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st);
+  return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st);
 }
 
 template <int MODE>
