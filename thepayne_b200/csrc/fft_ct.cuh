@@ -118,14 +118,33 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
   }
 }
 
+// The last strided pass works on blocks of 16*R points; thread tid + kNT*i of that pass owns
+// block (tid>>4) + (kNT/16) i, i.e. warp w owns blocks {2w, 2w+1} + (kNT/16) i.  When the
+// contiguous pass visits the 16-point groups in the SAME per-warp order, the two passes only need
+// __syncwarp() between them (kWarpLocal): two block barriers fewer per transform.
+template <int LOG2M>
+struct CtLast {
+  using P = CtPlan<LOG2M>;
+  static constexpr int LRL = P::n > 0 ? P::lr(P::n - 1) : 0;          // log2 radix of the last strided pass
+  static constexpr int NG = 1 << (LOG2M - 4);                          // 16-point groups
+  static constexpr bool kWarpLocal = P::n > 0 && (NG % kNT == 0) && ((1 << (LOG2M - LRL)) % kNT == 0);
+};
+
 template <int LOG2M, bool INV>
 __device__ __forceinline__ void ct_contiguous16(float2* z, int tid) {
   float4* z4 = reinterpret_cast<float4*>(z);
-  constexpr int NG = 1 << (LOG2M - 4);
+  using CL = CtLast<LOG2M>;
+  constexpr int NG = CL::NG;
 #pragma unroll
   for (int i = 0; i < (NG + kNT - 1) / kNT; ++i) {
-    const int g = tid + kNT * i;
+    int g = tid + kNT * i;
     if (NG % kNT != 0 && g >= NG) break;
+    if constexpr (CL::kWarpLocal) {
+      constexpr int R = 1 << CL::LRL;                 // groups per block
+      const int w = tid >> 5, idx = (tid & 31) + 32 * i;
+      const int bl = idx >> CL::LRL, sub = idx & (R - 1);
+      g = ((2 * w + (bl & 1) + (kNT / 16) * (bl >> 1)) << CL::LRL) + sub;
+    }
     float4* p = z4 + 8 * g;
     const int x = g & 7;
     float2 v[16];
@@ -144,18 +163,20 @@ __device__ __forceinline__ void ct_contiguous16(float2* z, int tid) {
 template <int LOG2M>
 __device__ __forceinline__ void ct_fft_forward(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
   using P = CtPlan<LOG2M>;
-  if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, false>(z, tw, tc, tid); __syncthreads(); }
-  if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, false>(z, tw, tc, tid); __syncthreads(); }
-  if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, false>(z, tw, tc, tid); __syncthreads(); }
-  if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, false>(z, tw, tc, tid); __syncthreads(); }
+  constexpr bool WL = CtLast<LOG2M>::kWarpLocal;
+  if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, false>(z, tw, tc, tid); if (WL && P::n == 1) __syncwarp(); else __syncthreads(); }
+  if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, false>(z, tw, tc, tid); if (WL && P::n == 2) __syncwarp(); else __syncthreads(); }
+  if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, false>(z, tw, tc, tid); if (WL && P::n == 3) __syncwarp(); else __syncthreads(); }
+  if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, false>(z, tw, tc, tid); if (WL && P::n == 4) __syncwarp(); else __syncthreads(); }
   ct_contiguous16<LOG2M, false>(z, tid);
   __syncthreads();
 }
 template <int LOG2M>
 __device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
   using P = CtPlan<LOG2M>;
+  constexpr bool WL = CtLast<LOG2M>::kWarpLocal;
   ct_contiguous16<LOG2M, true>(z, tid);
-  __syncthreads();
+  if (WL) __syncwarp(); else __syncthreads();
   if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, true>(z, tw, tc, tid); __syncthreads(); }
   if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, true>(z, tw, tc, tid); __syncthreads(); }
   if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, true>(z, tw, tc, tid); __syncthreads(); }
