@@ -368,12 +368,23 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     }
   }
   if (l2 <= 15) {
-    CU_TRY(cudaFuncSetAttribute(payne::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)c->tail_smem));
     int occ = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_kernel, payne::kTailThreads,
-                                                         c->tail_smem));
-    if (occ < 1) return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+#define PAYNE_GEN_CASE(L)                                                                              \
+    case L:                                                                                            \
+      e1 = cudaFuncSetAttribute(payne::tail_general_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)c->tail_smem);                                                    \
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_general_kernel<L>,          \
+                                                         payne::kTailThreads, c->tail_smem);           \
+      break;
+    switch (l2 < 10 ? 10 : l2) {
+      PAYNE_GEN_CASE(10) PAYNE_GEN_CASE(11) PAYNE_GEN_CASE(12) PAYNE_GEN_CASE(13) PAYNE_GEN_CASE(14)
+      PAYNE_GEN_CASE(15)
+      default: break;
+    }
+#undef PAYNE_GEN_CASE
+    if (e1 != cudaSuccess || e2 != cudaSuccess || occ < 1)
+      return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
     c->tail_grid = occ * c->sm_count;
   } else if (!c->use_fast) {
     return fail(PAYNE_E_UNSUPPORTED,
@@ -533,7 +544,15 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         }
       } else {
         if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
-        tail_kernel<<<std::min(c->tail_grid, nb), kTailThreads, c->tail_smem, st>>>(T);
+        const int grid = std::min(c->tail_grid, nb);
+        switch (T.log2N1 < 10 ? 10 : T.log2N1) {
+          case 10: tail_general_kernel<10><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+          case 11: tail_general_kernel<11><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+          case 12: tail_general_kernel<12><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+          case 13: tail_general_kernel<13><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+          case 14: tail_general_kernel<14><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+          default: tail_general_kernel<15><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
+        }
       }
       c->launches++;
     } else if (lnl) {

@@ -14,6 +14,7 @@
 #pragma once
 #include "fft_ct.cuh"
 #include "tail.cuh"
+#include "tail_general.cuh"
 
 namespace payne {
 
@@ -257,18 +258,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       } else {
         stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
         __syncthreads();
-        constexpr int LA = kSplit ? 15 : LOG2N1;            // largest all-in-smem transform here
-        if (log2N2 == LA) {
-          ct_convolve<LA - 1>(z, tw, F.twc, H, tid);
-        } else if (LA >= 10 && log2N2 == LA - 1) {
-          ct_convolve<(LA >= 10 ? LA - 2 : 8)>(z, tw, F.twc, H, tid);
-        } else {
-          const Twiddles twr{P.tw, P.log2tw};
-          FftPlan plan; plan.make(log2N2 - 1);
-          fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
-          filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
-          fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
-        }
+        convolve_any<LOG2N1>(z, log2N2, tw, F.twc, H, tid);
         acc = final_pass(P, F, S, FS, zs, tid, p, N2);
       }
     } else {
