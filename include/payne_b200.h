@@ -139,7 +139,8 @@ int payne_lnlike_batch_host(PayneCtx* ctx, const double* theta_host, int64_t B, 
 int payne_model_batch(PayneCtx* ctx, const double* theta_dev, int64_t B, int64_t ld,
                       double* flux_dev, double* mags_dev, double* lnl_dev, void* stream);
 
-/* Emulator forward pass only.  x_dev: [B, D_in] fp64 labels; y_dev: [B, ldy] fp32, ldy>=D_out. */
+/* Emulator forward pass only.  x_dev: [B, D_in] fp64 labels; y_dev: [B, ldy] fp32, ldy>=D_out.
+ * Tensor-core precisions write y with TMA stores: y_dev 16-byte aligned, ldy a multiple of 4. */
 int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, int64_t ldy,
                    void* stream);
 

@@ -102,6 +102,55 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// TMA store of a shared-memory box (128B-swizzled) into the output tensor; out-of-range rows /
+// columns of the box are clipped by the tensor map.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+// ---- cta_group::2 (two SMs on one tile) ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even CTA
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arrive on the even CTA's barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -180,6 +229,39 @@ constexpr int kTcThreads = 256;
 constexpr int kBM = 128;
 constexpr int kRowBytes = 128;   // one swizzle row: 32 tf32 or 64 bf16 along K
 
+// Epilogue of one 32-row x 32-column block for the fp32 output layer: (main [+ corr]) * scale +
+// bias, written as 16-byte chunks into a 128B-swizzled staging block and stored by TMA.
+//   stage : this warp's 4 KB staging block (1024-byte aligned);  sb / ss : bias and scale of the
+//   tile's columns in shared memory;  lane = row of the block.
+template <bool X3>
+__device__ __forceinline__ void epi_store_block(const CUtensorMap* cmap, float* stage, const float* sb,
+                                                const float* ss, const uint32_t (&v)[32], const uint32_t (&c)[32],
+                                                int colbase, int gcol0, int grow0, int lane) {
+  if (lane == 0) ptx::tma_store_wait_read();      // the previous store has finished reading the block
+  __syncwarp();
+  float4* st4 = reinterpret_cast<float4*>(stage) + lane * 8;
+  const float4* b4 = reinterpret_cast<const float4*>(sb + colbase);
+  const float4* s4 = reinterpret_cast<const float4*>(ss + colbase);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 bb = b4[k], sc = s4[k];
+    float4 o;
+    if (X3) {
+      o.x = fmaf(__uint_as_float(v[4 * k + 0]) + __uint_as_float(c[4 * k + 0]), sc.x, bb.x);
+      o.y = fmaf(__uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1]), sc.y, bb.y);
+      o.z = fmaf(__uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]), sc.z, bb.z);
+      o.w = fmaf(__uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]), sc.w, bb.w);
+    } else {
+      o.x = __uint_as_float(v[4 * k + 0]) + bb.x; o.y = __uint_as_float(v[4 * k + 1]) + bb.y;
+      o.z = __uint_as_float(v[4 * k + 2]) + bb.z; o.w = __uint_as_float(v[4 * k + 3]) + bb.w;
+    }
+    st4[k ^ (lane & 7)] = o;                      // 128B swizzle: chunk index XOR (row mod 8)
+  }
+  ptx::fence_async_smem();
+  __syncwarp();
+  if (lane == 0) ptx::tma_store_2d(cmap, stage, gcol0, grow0);
+}
+
 template <int BN, int MODE>
 struct TcCfg {
   static constexpr int kPlanes = MODE == kModeX3 ? 3 : (MODE == kModeT3 ? 2 : 1);
@@ -191,7 +273,8 @@ struct TcCfg {
   static constexpr int kPatchBytes = 4 * 32 * 33 * 4;
   static constexpr int kBudget = 220 * 1024 - kPatchBytes - 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
-  static constexpr int kSmem = kStages * kStageBytes + kPatchBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + kPatchBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                               2 * BN * 4 /*bias, scale*/;
   static constexpr int kAccCols = MODE == kModeX3 ? 2 * BN : BN;  // columns per accumulator set
   static constexpr int kTmemCols = 2 * kAccCols;                  // double buffered
   static_assert(kTmemCols <= 512, "TMEM budget");
@@ -200,6 +283,7 @@ struct TcCfg {
 struct TcMaps {
   CUtensorMap a[3];
   CUtensorMap b[3];
+  CUtensorMap c;       // EPI 0: fp32 output [M, N] (pitch ldc), boxes of 32 x 32, 128B swizzle
 };
 
 struct TcGemmArgs {
@@ -232,6 +316,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   uint64_t* tfull = bars + 2 * NS;       // [2]
   uint64_t* tempty = bars + 2 * NS + 2;  // [2]
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * NS + 4);
+  float* sbias = (float*)(bars + 32);    // 256 bytes reserved for barriers
+  float* sscale = sbias + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_true = (G.M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
@@ -331,14 +417,37 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   } else if (warp >= 4) {
     // ===================== epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31)
     const int q = warp & 3;
-    float* pt = patch + q * (32 * 33);
+    float* pt = patch + q * (EPI == 0 ? 1024 : 32 * 33);     // EPI 0: 4 KB swizzled staging block
     int acc = 0; uint32_t aph = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
+      if constexpr (EPI == 0) {
+        // bias (+shift) and scale of this tile's columns -> shared memory, before the accumulator
+        // is awaited so the loads are off the critical path
+        ptx::epi_bar_sync();                       // previous tile's readers are done
+        for (int cix = threadIdx.x - 128; cix < BN; cix += 128) {
+          const int gc = n0 + cix;
+          sbias[cix] = (gc < G.N ? __ldg(G.bias + gc) : 0.f) + G.bias_shift;
+          sscale[cix] = (MODE == kModeX3 && gc < G.N) ? __ldg(G.wscale + gc) : 1.f;
+        }
+        ptx::epi_bar_sync();
+      }
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
       const int row_base = m0 + q * 32;
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols);
+      if constexpr (EPI == 0) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int col0 = n0 + ch * 32;
+          if (col0 >= G.N) break;
+          uint32_t v[32], c[32];
+          ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
+          if constexpr (MODE == kModeX3) ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
+          ptx::tmem_ld_wait();
+          epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
+        }
+      } else {
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col0 = n0 + ch * 32;
@@ -387,16 +496,173 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
         }
         __syncwarp();
       }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
+    if (EPI == 0 && lane == 0) ptx::tma_store_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (MC) ptx::cluster_sync_all();          // no multicast / remote commit may target a CTA that has left
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lin6 on CTA PAIRS (cta_group::2): a 2-CTA cluster owns a 256 x 256 output tile; CTA r holds rows
+// [128 r, 128 r + 128) of the activations and weight rows [128 r, +128) of the tile, the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) and each SM accumulates its 128 rows in its own
+// TMEM.  Inbound operand traffic per SM halves relative to the 128 x 128 single-CTA tiles
+// (96 KB per 3072 MMA-cycles instead of per 1536), which is what bounds this K = 256 GEMM.
+// X3 only: the two accumulators take all 512 TMEM columns, so the epilogue is not overlapped.
+__host__ __device__ constexpr uint32_t umma_idesc_m256(int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
+  constexpr int BN = 256, BNH = 128, NP = 3, NS = 2;
+  constexpr int kABytes = kBM * kRowBytes, kBBytes = BNH * kRowBytes;
+  constexpr int kStageBytes = NP * (kABytes + kBBytes);          // per CTA
+  constexpr int kBK = 64;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* stages = base;
+  float* patch = (float*)(base + NS * kStageBytes);
+  uint64_t* bars = (uint64_t*)((unsigned char*)patch + 4 * 32 * 33 * 4);
+  uint64_t* full = bars;             // [NS]  used in the leader: 2 arrivals + bytes of both CTAs
+  uint64_t* empty = bars + NS;       // [NS]  per CTA: multicast commit of the leader
+  uint64_t* tfull = bars + 2 * NS;   // per CTA: multicast commit of the leader
+  uint64_t* tempty = tfull + 1;      // leader: 8 epilogue warps (both CTAs)
+  uint32_t* tmem_ptr = (uint32_t*)(tempty + 1);
+  float* sbias = (float*)(bars + 32);
+  float* sscale = sbias + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader = crank == 0;
+  const int num_mp = (G.M + 255) / 256, num_n = (G.N + BN - 1) / BN;
+  const int num_tiles = num_mp * num_n;
+  const int num_kb = (G.K + kBK - 1) / kBK;
+  const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < NP; ++p) { ptx::prefetch_tmap(&T.a[p]); ptx::prefetch_tmap(&T.b[p]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 2); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tfull, 1);
+    ptx::mbar_init(tempty, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs); bytes and arrivals go to the leader's barrier
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const int m0 = (tile / num_n) * 256 + (int)crank * 128, n0 = (tile % num_n) * BN + (int)crank * BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait_cluster(&empty[s], ph ^ 1);
+          unsigned char* st = stages + s * kStageBytes;
+          if (leader) ptx::mbar_expect_tx(&full[s], 2 * kStageBytes);
+          const int k0 = kb * kBK;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            ptx::tma_load_2d_2sm(&T.a[p], &full[s], st + p * kABytes, k0, m0);
+            ptx::tma_load_2d_2sm(&T.b[p], &full[s], st + NP * kABytes + p * kBBytes, k0, n0);
+          }
+          if (!leader) ptx::mbar_arrive_leader(&full[s]);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_m256(BN, 1u);
+      int s = 0; uint32_t ph = 0;
+      uint32_t aph = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        ptx::mbar_wait_cluster(tempty, aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait_cluster(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t st = ptx::smem_u32(stages + s * kStageBytes);
+          uint64_t da[3], db[3];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            da[p] = umma_desc_k_sw128(st + p * kABytes);
+            db[p] = umma_desc_k_sw128(st + NP * kABytes + p * kBBytes);
+          }
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks) {
+            const uint64_t ko = (uint64_t)((ks * 32) >> 4);
+            const uint32_t first = (kb | ks) != 0;
+            ptx::mma_bf16_2sm(d_main, da[0] + ko, db[0] + ko, idesc, first);
+            ptx::mma_bf16_2sm(d_corr, da[0] + ko, db[2] + ko, idesc, first);
+            ptx::mma_bf16_2sm(d_corr, da[1] + ko, db[1] + ko, idesc, 1);
+            ptx::mma_bf16_2sm(d_corr, da[2] + ko, db[0] + ko, idesc, 1);
+            ptx::mma_bf16_2sm(d_corr, da[0] + ko, db[1] + ko, idesc, 1);
+            ptx::mma_bf16_2sm(d_corr, da[1] + ko, db[0] + ko, idesc, 1);
+          }
+          ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)3);
+          if (kb == num_kb - 1) ptx::mma_commit_2sm_mc(tfull, (uint16_t)3);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+        aph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    float* pt = patch + q * 1024;
+    uint32_t aph = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+      const int m0 = (tile / num_n) * 256 + (int)crank * 128, n0 = (tile % num_n) * BN;
+      ptx::epi_bar_sync();
+      for (int cix = threadIdx.x - 128; cix < BN; cix += 128) {
+        const int gc = n0 + cix;
+        sbias[cix] = (gc < G.N ? __ldg(G.bias + gc) : 0.f) + G.bias_shift;
+        sscale[cix] = gc < G.N ? __ldg(G.wscale + gc) : 1.f;
+      }
+      ptx::epi_bar_sync();
+      ptx::mbar_wait_cluster(tfull, aph);
+      ptx::tc_fence_after();
+      const int row_base = m0 + q * 32;
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n0 + ch * 32;
+        if (col0 >= G.N) break;
+        uint32_t v[32], c[32];
+        ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
+        ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
+        ptx::tmem_ld_wait();
+        epi_store_block<true>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(tempty);
+      aph ^= 1;
+    }
+    if (lane == 0) ptx::tma_store_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
 }
 
 // fp32 -> operand planes of the next GEMM
@@ -440,6 +706,21 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // 2-D row-major [rows, K] (pitch ld elements) -> boxes of {128 bytes of K, box_rows}, 128B swizzle
+// fp32 output [rows, cols] with pitch ld floats -> 32 x 32 boxes, 128B swizzle (TMA store)
+inline int make_tmap_out(CUtensorMap* m, const void* ptr, long long rows, int cols, long long ld) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return PAYNE_E_CUDA;
+  if ((ld & 3) || ((uintptr_t)ptr & 15)) return PAYNE_E_INVALID;   // TMA: 16-byte base and pitch
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PAYNE_OK : PAYNE_E_CUDA;
+}
+
 inline int make_tmap(CUtensorMap* m, const void* ptr, long long rows, int K, long long ld, int box_rows,
                      int elem_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -533,6 +814,8 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
     if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, MC ? BN / 2 : BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
   }
   for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
+  if (EPI == 0) { if (int rc = make_tmap_out(&T.c, out0, M, W.N, ldc)) return rc; }
+  else T.c = T.a[0];
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -559,9 +842,46 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
+// PAYNE_GEMM_2SM=0 falls back to the single-CTA tiles for lin6.
+inline bool tc_2sm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PAYNE_GEMM_2SM"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
+inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, long long ldc,
+                         float bias_shift, int M, int sm_count, cudaStream_t st) {
+  constexpr int kSmem = 2 * 3 * (kBM * kRowBytes + 128 * kRowBytes) + 4 * 32 * 33 * 4 + 1024 + 256 + 2 * 256 * 4;
+  TcMaps T;
+  for (int p = 0; p < 3; ++p) {
+    if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, 2)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.b[p], W.xplane[p], W.N, K, W.Kp, 128, 2)) return PAYNE_E_CUDA;
+  }
+  if (int rc = make_tmap_out(&T.c, out0, M, W.N, ldc)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
+      return PAYNE_E_CUDA;
+    attr_set = true;
+  }
+  TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K};
+  const int pair_tiles = ((M + 255) / 256) * ((W.N + 255) / 256);
+  const int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<0>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
+}
+
 template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                      void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_enabled())
+    return tc_launch_2sm(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st);
   // multicast pays when many row tiles share each weight tile (the wide last layer)
   if (EPI == 0 && BN >= 128 && M > kBM && tc_multicast_enabled())
     return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st);

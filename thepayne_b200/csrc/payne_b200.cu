@@ -662,6 +662,8 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
   if (!c || !x_dev || !y_dev) return fail(PAYNE_E_INVALID, "null argument");
   if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
   if (ldy < c->D_out) return fail(PAYNE_E_INVALID, "ldy < D_out");
+  if (c->lay.precision != PAYNE_PREC_SIMT_FP32 && ((ldy & 3) || ((uintptr_t)y_dev & 15)))
+    return fail(PAYNE_E_INVALID, "y_dev must be 16-byte aligned with ldy a multiple of 4 (TMA store)");
   if (B <= 0) return PAYNE_OK;
   CU_TRY(cudaSetDevice(c->device));
   int rc = ensure_workspace(c, B);
