@@ -36,7 +36,7 @@ struct CtPlan {
   __host__ __device__ static constexpr int log2L(int i) {   // sub-transform length entering pass i
     return i == 0 ? LOG2M : i == 1 ? LOG2M - r0 : i == 2 ? LOG2M - r0 - r1 : LOG2M - r0 - r1 - r2;
   }
-  __device__ static __forceinline__ int row_of(int klo) {
+  __host__ __device__ static constexpr int row_of(int klo) {
     int row = 0;
     int l = LOG2M - 4;
     if (r0 > 0) { l -= r0; row += (klo & ((1 << r0) - 1)) << l; klo >>= r0; }
@@ -52,9 +52,31 @@ struct TwConst {
   float2 c[2][4][16];   // [log2M - 13][ip][q]
 };
 
+// Compact per-pass twiddle tables.  The factors W_L^{jq} a thread hoists for one strided pass are
+// scattered over the main table (one useful 8 bytes per 128-byte line: 7 line fetches per thread,
+// a >100 KB line footprint that the ~30 KB of L1 left beside the transform buffers cannot hold, so
+// every pass started with L2-latency loads).  Here they are laid out [pass][j][q], q fastest: a
+// thread reads R consecutive float2 (64 or 128 bytes), a warp 2-4 KB contiguous, and the whole
+// set for one transform size is 25-42 KB.  Values are copies of main-table entries (bit-identical).
+template <int LOG2M>
+struct CtTwLayout {
+  using P = CtPlan<LOG2M>;
+  __host__ __device__ static constexpr int J(int p) {          // distinct j per pass held by a CTA
+    const int S = 1 << (P::log2L(p) - P::lr(p));
+    return S < kNT ? S : kNT;
+  }
+  __host__ __device__ static constexpr int off(int p) {        // float2 offset of pass p
+    int o = 0;
+    for (int i = 0; i < p; ++i) o += J(i) << P::lr(i);
+    return o;
+  }
+  static constexpr int total = off(P::n);
+};
+
 struct TwTab {
   const float2* __restrict__ tab;   // exp(-2 pi i e / 2^log2n), e < 2^(log2n-1)
   int log2n;
+  const float2* const* pass;        // pass[LOG2M] -> CtTwLayout<LOG2M> table (device pointers, in param space)
 };
 
 template <int LOG2L>
@@ -62,7 +84,11 @@ __device__ __forceinline__ float2 tw_load(const TwTab& tw, int x) {   // W_L^x, 
   const int sh = tw.log2n - LOG2L;
   const int e = x << sh;
   const int half = 1 << (tw.log2n - 1);
+#if defined(PAYNE_FFT_VARIANT) && PAYNE_FFT_VARIANT == 3     // microbenchmark: no table access
+  float2 w = make_float2(__int_as_float(0x3f800000 | (e & 0xffff)), 0.5f);
+#else
   float2 w = __ldg(tw.tab + (e & (half - 1)));
+#endif
   if (e & half) { w.x = -w.x; w.y = -w.y; }
   return w;
 }
@@ -78,8 +104,20 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
   static_assert(SPAN == 1 || (PASS == 0 && LOG2M >= 13 && LOG2M <= 14), "constant table covers log2M 13..14");
   const int jb = tid & (S - 1);
   float2 wb[R];
+#if defined(PAYNE_FFT_VARIANT) && PAYNE_FFT_VARIANT == 4     // microbenchmark: scattered main-table loads
 #pragma unroll
   for (int q = 1; q < R; ++q) wb[q] = tw_load<LOG2L>(tw, jb * q);
+#else
+  {
+    const float4* pt = reinterpret_cast<const float4*>(tw.pass[LOG2M] + CtTwLayout<LOG2M>::off(PASS) + (jb << LR));
+#pragma unroll
+    for (int q = 0; q < R; q += 2) {
+      const float4 u = __ldg(pt + (q >> 1));
+      wb[q] = make_float2(u.x, u.y);
+      wb[q + 1] = make_float2(u.z, u.w);
+    }
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int g = tid + kNT * i;
@@ -89,11 +127,20 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
     float2 v[R];
     // stride >= 128 points: adding m*S never touches the bits the swizzle reads or flips
     const int sbase = swz(base);
+#if defined(PAYNE_FFT_VARIANT) && PAYNE_FFT_VARIANT == 2     // microbenchmark: math only
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = make_float2(__int_as_float(sbase + m), __int_as_float(base - m));
+#else
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = (LOG2S >= 7) ? z[sbase + (m << LOG2S)] : z[swz(base + (m << LOG2S))];
+#endif
     constexpr int kSet = LOG2M >= 13 ? LOG2M - 13 : 0;
     const int ip = i % SPAN;
+#if defined(PAYNE_FFT_VARIANT) && PAYNE_FFT_VARIANT == 1     // microbenchmark: memory traffic only
+    if (false) {
+#else
     if constexpr (!INV) {
+#endif
       dftR<R, false>(v);
 #pragma unroll
       for (int q = 1; q < R; ++q) {
@@ -110,11 +157,18 @@ __device__ __forceinline__ void ct_strided_pass(float2* z, const TwTab& tw, cons
       }
       dftR<R, true>(v);
     }
+#if defined(PAYNE_FFT_VARIANT) && PAYNE_FFT_VARIANT == 2
+    float2 acc = v[0];
+#pragma unroll
+    for (int m = 1; m < R; ++m) acc = acc + v[m];
+    if (acc.x == 1.2345f) z[sbase] = acc;          // keeps the math alive, never true in practice
+#else
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       if (LOG2S >= 7) z[sbase + (m << LOG2S)] = v[m];
       else z[swz(base + (m << LOG2S))] = v[m];
     }
+#endif
   }
 }
 
@@ -186,38 +240,80 @@ __device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const
 // Filter stage on digit-reversed storage; H(k), k in [0, M], includes the 1/M of the inverse.
 // Work item w = tid + kNT i  ->  (klo = w >> 4, c = w & 15): c is fixed per thread, so the factor
 // exp(-2 pi i c / 32) of the untangling twiddle W_N^k, k = klo + c M/16, is a per-thread constant.
+// One pair (k, M-k) of the filter stage: z[pk] holds Z_k, z[pp] holds Z_{M-k}; W = exp(-2 pi i k / N).
+template <class HF>
+__device__ __forceinline__ void ct_filter_one(float2* z, int pk, int pp, float2 W, float hk, float hm) {
+  const float2 Zk = z[pk], Zp = z[pp];
+  const float A = 0.5f * (hk + hm), Bc = 0.5f * (hk - hm);
+  const float2 E = make_float2(0.5f * (Zk.x + Zp.x), 0.5f * (Zk.y - Zp.y));
+  const float2 O = make_float2(0.5f * (Zk.y + Zp.y), -0.5f * (Zk.x - Zp.x));
+  const float2 WO = cmul(W, O), WcE = cmulc(E, W);
+  const float2 E2 = make_float2(A * E.x + Bc * WO.x, A * E.y + Bc * WO.y);
+  const float2 O2 = make_float2(Bc * WcE.x + A * O.x, Bc * WcE.y + A * O.y);
+  z[pk] = make_float2(E2.x - O2.y, E2.y + O2.x);
+  if (pp != pk) z[pp] = make_float2(E2.x + O2.y, O2.x - E2.y);
+}
+
 template <int LOG2M, class HF>
 __device__ __forceinline__ void ct_filter_pairs(float2* z, const TwTab& tw, const HF& H, int tid) {
   using P = CtPlan<LOG2M>;
   constexpr int M = 1 << LOG2M, Mlo = M >> 4;
-  constexpr int NITEMS = ((Mlo >> 1) + 1) << 4;
   const int c = tid & 15;
   const float2 wc = tw_load<5>(tw, c);                  // exp(-2 pi i c / 32)
-#pragma unroll 2
-  for (int w = tid; w < NITEMS; w += kNT) {
-    const int klo = w >> 4;
-    int klo_p, c_p;
-    if (klo == 0) {
-      if (c > 8) continue;
-      klo_p = 0; c_p = (16 - c) & 15;
-    } else {
-      klo_p = Mlo - klo; c_p = 15 - c;
-      if (klo_p == klo && c > 7) continue;
+  if constexpr (Mlo >= 2 * kNT / 16 * 1 && (Mlo % (2 * kNT / 16)) == 0) {
+    // klo = kb + 16 i with kb = tid >> 4 < 16: the digit reversal is a bit permutation, so
+    // row_of(klo) = row_of(kb) + row_of(16 i) and the second term (like the storage swizzle,
+    // which only reads row bits that come from i) folds to a constant once the loop is unrolled.
+    // The partner klo' = Mlo - klo = ((16 - kb) & 15) + 16 (Mlo/16 - 1 - i + (kb == 0)).
+    constexpr int KB = kNT / 16, NI = Mlo / (2 * KB);
+    static_assert(KB == 16, "item mapping assumes 256 threads");
+    const int kb = tid >> 4;
+    const int rk = P::row_of(kb), rq = P::row_of((KB - kb) & (KB - 1));
+    const bool kb0 = (kb == 0);
+    const int sh = tw.log2n - (LOG2M + 1);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int klo = kb + KB * i;
+      const int k = klo + (c << (LOG2M - 4));
+      const float2 W = cmul(__ldg(tw.tab + (klo << sh)), wc);       // exp(-2 pi i k / N); klo < N/4
+      const float hk = H(k), hm = H(M - k);
+      const int row = rk + P::row_of(KB * i);
+      int rowp, c_p;
+      if (i == 0) {
+        // kb == 0: the pair lives inside row 0 (k' = M - k <-> c' = 16 - c); c > 8 already done by c' < 8
+        rowp = kb0 ? 0 : rq + P::row_of(KB * (Mlo / KB - 1));
+        c_p = kb0 ? ((16 - c) & 15) : 15 - c;
+        if (kb0 && c > 8) continue;
+      } else {
+        rowp = kb0 ? P::row_of(Mlo - KB * i) : rq + P::row_of(KB * (Mlo / KB - 1 - i));
+        c_p = 15 - c;
+      }
+      ct_filter_one<HF>(z, swz((row << 4) + c), swz((rowp << 4) + c_p), W, hk, hm);
     }
-    const int k = klo + (c << (LOG2M - 4));
-    const int pk = swz((P::row_of(klo) << 4) + c);
-    const int pp = swz((P::row_of(klo_p) << 4) + c_p);
-    const float2 Zk = z[pk], Zp = z[pp];
-    const float2 W = cmul(tw_load<LOG2M + 1>(tw, klo), wc);   // exp(-2 pi i k / N)
-    const float hk = H(k), hm = H(M - k);
-    const float A = 0.5f * (hk + hm), Bc = 0.5f * (hk - hm);
-    const float2 E = make_float2(0.5f * (Zk.x + Zp.x), 0.5f * (Zk.y - Zp.y));
-    const float2 O = make_float2(0.5f * (Zk.y + Zp.y), -0.5f * (Zk.x - Zp.x));
-    const float2 WO = cmul(W, O), WcE = cmulc(E, W);
-    const float2 E2 = make_float2(A * E.x + Bc * WO.x, A * E.y + Bc * WO.y);
-    const float2 O2 = make_float2(Bc * WcE.x + A * O.x, Bc * WcE.y + A * O.y);
-    z[pk] = make_float2(E2.x - O2.y, E2.y + O2.x);
-    if (pp != pk) z[pp] = make_float2(E2.x + O2.y, O2.x - E2.y);
+    if (tid < 8) {                                       // klo = Mlo/2 pairs with itself: c <-> 15 - c
+      constexpr int klo = Mlo / 2;
+      const int k = klo + (c << (LOG2M - 4));
+      const float2 W = cmul(__ldg(tw.tab + (klo << sh)), wc);
+      constexpr int row = P::row_of(klo);
+      ct_filter_one<HF>(z, swz((row << 4) + c), swz((row << 4) + 15 - c), W, H(k), H(M - k));
+    }
+  } else {
+    constexpr int NITEMS = ((Mlo >> 1) + 1) << 4;
+#pragma unroll 2
+    for (int w = tid; w < NITEMS; w += kNT) {
+      const int klo = w >> 4;
+      int klo_p, c_p;
+      if (klo == 0) {
+        if (c > 8) continue;
+        klo_p = 0; c_p = (16 - c) & 15;
+      } else {
+        klo_p = Mlo - klo; c_p = 15 - c;
+        if (klo_p == klo && c > 7) continue;
+      }
+      const int k = klo + (c << (LOG2M - 4));
+      const float2 W = cmul(tw_load<LOG2M + 1>(tw, klo), wc);   // exp(-2 pi i k / N)
+      ct_filter_one<HF>(z, swz((P::row_of(klo) << 4) + c), swz((P::row_of(klo_p) << 4) + c_p), W, H(k), H(M - k));
+    }
   }
   __syncthreads();
 }
@@ -303,6 +399,28 @@ __device__ __forceinline__ void ct_convolve(float2* z, const TwTab& tw, const Tw
   ct_fft_forward<LOG2M>(z, tw, tc, tid);
   ct_filter_pairs<LOG2M>(z, tw, H, tid);
   ct_fft_inverse<LOG2M>(z, tw, tc, tid);
+}
+
+// Host side: fill the CtTwLayout<LOG2M> table from a function w(x, log2L) = W_L^x.
+template <int LOG2M, class WF>
+inline void ct_build_pass_table(float2* out, WF&& w) {
+  using P = CtPlan<LOG2M>;
+  using Lay = CtTwLayout<LOG2M>;
+  for (int p = 0; p < P::n; ++p) {
+    const int lr = P::lr(p), R = 1 << lr, log2L = P::log2L(p), L = 1 << log2L;
+    for (int j = 0; j < Lay::J(p); ++j)
+      for (int q = 0; q < R; ++q) out[Lay::off(p) + (j << lr) + q] = w((int)(((long long)j * q) & (L - 1)), log2L);
+  }
+}
+template <class WF>
+inline int ct_pass_table(int log2m, float2* out, WF&& w) {     // returns the table length; out may be null
+#define PAYNE_PT_CASE(L) case L: if (out) ct_build_pass_table<L>(out, w); return CtTwLayout<L>::total;
+  switch (log2m) {
+    PAYNE_PT_CASE(6) PAYNE_PT_CASE(7) PAYNE_PT_CASE(8) PAYNE_PT_CASE(9) PAYNE_PT_CASE(10) PAYNE_PT_CASE(11)
+    PAYNE_PT_CASE(12) PAYNE_PT_CASE(13) PAYNE_PT_CASE(14)
+    default: return 0;
+  }
+#undef PAYNE_PT_CASE
 }
 
 }  // namespace payne

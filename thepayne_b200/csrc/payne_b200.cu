@@ -131,6 +131,7 @@ struct PayneCtx {
   payne::TailParams tail{};
   payne::FastGrid fast{};
   size_t tail_smem = 0;
+  size_t fast_smem = 0;      // tail_smem + rotation-table window (fast kernels)
   int tail_grid = 0, tail_grid_fast = 0;
   int grid_loguniform = 0;
   int use_fast = 0;        // analytic-regrid tail selected (log-uniform emulator grid)
@@ -261,6 +262,25 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   float2* dtw;
   rc = upload_owned(c, &dtw, tw.data(), tw.size()); if (rc) return rc;
   T.tw = dtw; T.log2tw = l2; T.max_log2N = l2;
+  // compact per-pass copies for the compile-time-planned transforms (fft_ct.cuh, CtTwLayout)
+  {
+    auto wfun = [&](int x, int log2L) {
+      const int e = x << (l2 - log2L);
+      if (e < N1 / 2) return tw[e];
+      const float2 t = tw[e - N1 / 2];
+      return make_float2(-t.x, -t.y);
+    };
+    for (int m = 0; m < 16; ++m) T.twpass[m] = nullptr;
+    for (int m = 6; m <= std::min(14, l2 - 1); ++m) {
+      const int len = payne::ct_pass_table(m, (float2*)nullptr, wfun);
+      if (len <= 0) continue;
+      std::vector<float2> pt(len);
+      payne::ct_pass_table(m, pt.data(), wfun);
+      float2* dpt;
+      rc = upload_owned(c, &dpt, pt.data(), pt.size()); if (rc) return rc;
+      T.twpass[m] = dpt;
+    }
+  }
   // one 8-byte slot per complex point; from 65536 samples on only half of them sit in shared
   // memory (split transform, fast tail only)
   c->tail_smem = l2 >= 16 ? (size_t)2 * N1 : (size_t)4 * N1;
@@ -343,22 +363,41 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
         }
   }
   if (c->use_fast) {
+    // Shared memory left over next to the transform buffer holds the slice of the rotation-kernel
+    // table a point actually uses (its lookups are scattered across lanes; from shared memory each
+    // costs one wavefront instead of one per touched line).  Take the largest slice that does not
+    // cost a resident CTA.
     int occf = 0;
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    auto probe = [&](size_t bytes, int* occ) {
 #define PAYNE_FAST_CASE(L)                                                                           \
-    case L:                                                                                          \
-      e1 = cudaFuncSetAttribute(payne::tail_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                (int)c->tail_smem);                                                  \
-      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, payne::tail_fast_kernel<L>, payne::kNT, \
-                                                         c->tail_smem);                              \
-      break;
-    switch (l2) {
-      PAYNE_FAST_CASE(10) PAYNE_FAST_CASE(11) PAYNE_FAST_CASE(12) PAYNE_FAST_CASE(13)
-      PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15) PAYNE_FAST_CASE(16)
-      default: break;
-    }
+      case L:                                                                                        \
+        e1 = cudaFuncSetAttribute(payne::tail_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)bytes);                                                       \
+        e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, payne::tail_fast_kernel<L>, payne::kNT, bytes); \
+        break;
+      switch (l2) {
+        PAYNE_FAST_CASE(10) PAYNE_FAST_CASE(11) PAYNE_FAST_CASE(12) PAYNE_FAST_CASE(13)
+        PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15) PAYNE_FAST_CASE(16)
+        default: break;
+      }
 #undef PAYNE_FAST_CASE
-    if (e1 != cudaSuccess || e2 != cudaSuccess || occf < 1) c->use_fast = 0;
+      return e1 == cudaSuccess && e2 == cudaSuccess;
+    };
+    int occ0 = 0;
+    const bool ok0 = probe(c->tail_smem, &occ0);
+    size_t win = 0;
+    if (ok0 && occ0 >= 1) {
+      for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)10240, (size_t)8192, (size_t)6144,
+                          (size_t)4096, (size_t)2048}) {
+        int o = 0;
+        if (probe(c->tail_smem + cand, &o) && o == occ0) { win = cand; break; }
+        e1 = e2 = cudaSuccess;
+      }
+    }
+    c->fast_smem = c->tail_smem + win;
+    c->fast.win_floats = (int)(win / 4);
+    probe(c->fast_smem, &occf);
     c->tail_grid_fast = occf * c->sm_count;
     if (c->use_fast && l2 >= 16) {
       float* sc = nullptr;
@@ -437,7 +476,8 @@ int ensure_workspace(PayneCtx* c, long long B) {
   const long long need = std::min(B, c->slab);
   if (need <= c->slab_alloc) return PAYNE_OK;
   auto drop = [&](void* p) { if (p) cudaFree(p); };
-  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed);
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
+  c->fast.points = nullptr;
   payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
   c->flux = c->hA = c->hB = nullptr; c->chi2_sed = nullptr; c->slab_alloc = 0;
   const long long rows = (need + 127) / 128 * 128;
@@ -446,6 +486,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
     CU_TRY(cudaMalloc((void**)&c->flux, (size_t)rows * c->ldf * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
+    CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
     int rc = payne::tc_alloc_acts(&c->actA, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
     rc = payne::tc_alloc_acts(&c->actB, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
   }
@@ -533,14 +574,16 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       T.status = c->status;
       if (c->use_fast && c->allow_fast && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
+        tail_setup_kernel<<<(nb + 63) / 64, 64, 0, st>>>(T, c->fast);
+        c->launches++;
         switch (T.log2N1) {
-          case 10: tail_fast_kernel<10><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          case 11: tail_fast_kernel<11><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          case 12: tail_fast_kernel<12><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          case 13: tail_fast_kernel<13><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          case 14: tail_fast_kernel<14><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          case 15: tail_fast_kernel<15><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
-          default: tail_fast_kernel<16><<<grid, kNT, c->tail_smem, st>>>(T, c->fast); break;
+          case 10: tail_fast_kernel<10><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          case 11: tail_fast_kernel<11><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          case 12: tail_fast_kernel<12><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          case 13: tail_fast_kernel<13><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          case 14: tail_fast_kernel<14><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          case 15: tail_fast_kernel<15><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
+          default: tail_fast_kernel<16><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
         }
       } else {
         if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
@@ -608,7 +651,8 @@ void payne_ctx_destroy(PayneCtx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->owned) cudaFree(p);
   auto drop = [&](void* p) { if (p) cudaFree(p); };
-  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->status);
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
+  c->fast.points = nullptr; drop(c->status);
   payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
   drop(c->theta_stage); drop(c->lnl_stage);
   if (c->theta_pin) cudaFreeHost(c->theta_pin);
@@ -717,6 +761,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   }
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
+  if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }   // profiling aid, see tail.cuh
   return fail(PAYNE_E_INVALID, "unknown key " + k);
 }
 

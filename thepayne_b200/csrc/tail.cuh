@@ -45,6 +45,7 @@ struct TailParams {
   // twiddles exp(-2 pi i e / Ntw), e < Ntw/2
   const float2* tw;
   int log2tw;
+  const float2* twpass[16]; // [log2 M] compact per-pass twiddle tables of the compile-time plans (fft_ct.cuh)
   int max_log2N;          // largest FFT the shared-memory carve-out holds
   // observation
   int n_obs;
@@ -73,6 +74,8 @@ struct TailParams {
   double* model_out;        // [B, n_obs] or null
   int* status;              // device flag: bit0 = a point needed a larger FFT than the carve-out
   int B;
+  int debug_skip;           // profiling aid (fast tail): bit0/1 skip the stage-1/2 transforms, bit2 the
+                            // regrids in, bit3 the regrid back, bit4 the final pass; results are garbage
 };
 
 struct PointSetup {
@@ -132,7 +135,7 @@ struct RotH {
     const float w0 = fp1 * fm1 * fm2 * 0.5f;
     const float w1 = -fp1 * f * fm2 * 0.5f;
     const float w2 = fp1 * f * fm1 * (1.f / 6.f);
-    return (wm * __ldg(t) + w0 * __ldg(t + 1) + w1 * __ldg(t + 2) + w2 * __ldg(t + 3)) * invM;
+    return (wm * t[0] + w0 * t[1] + w1 * t[2] + w2 * t[3]) * invM;   // global table or its shared-memory slice
   }
   static __device__ __noinline__ float direct(double u) {  // beyond the table: fp64 closed form
     if (u == 0.0) return 1.f;

@@ -28,6 +28,8 @@ struct FastGrid {
   double dlnw, inv_dlnw;
   const double* obs_q;                // [n_obs] (ln lambda_j - ln w_0) / dlnw
   const double* obs_otm1;             // [n_obs] (flux - 1)/eflux : r = depth/eflux - otm1
+  void* points;                       // [slab] FastPoint, written by tail_setup_kernel
+  int win_floats;                     // shared-memory window for the rotation-kernel table (floats)
   float* scratch;                     // [grid, N1/2] second half of split transforms (N1 = 65536)
   TwConst twc;
 };
@@ -37,6 +39,14 @@ struct FastSetup {
   float s_invden;
   double q0, scale;                   // final: p = (obs_q - q0) * scale
 };
+
+// Per-point setup, computed by tail_setup_kernel (one thread per point) ahead of the tail so that
+// no CTA of the tail idles behind a single thread's fp64 logarithms.
+struct alignas(16) FastPoint {
+  PointSetup S;
+  FastSetup FS;
+};
+static_assert(sizeof(FastPoint) % 16 == 0, "FastPoint is copied as int4");
 
 template <class T>
 __device__ __forceinline__ void divmod_init(int tid, int num, int den, int& j, int& rem) {
@@ -84,21 +94,30 @@ __device__ __forceinline__ void regrid_in(const float* row, const ZV& zv, int ti
   int j = (int)(v / den);
   int rem = (int)(v - (long long)j * den);
   j += j0;
-#pragma unroll 4
-  for (int k = 2 * tid; k < N; k += 2 * kNT) {
-    int rem1 = rem + num, j1 = j;
-    if (rem1 >= den) { rem1 -= den; ++j1; }
-    const float r0 = ld_depth<CLEAN>(row, j);
-    const float r1 = ld_depth<CLEAN>(row, min(j + 1, jlast));
-    const float r2 = ld_depth<CLEAN>(row, min(j + 2, jlast));
-    const bool same = (j1 == j);
+  int k = 2 * tid;
+  if (k >= N) return;
+  // the three row values of the NEXT pair are requested before the current pair is interpolated
+  float r0 = ld_depth<CLEAN>(row, j);
+  float r1 = ld_depth<CLEAN>(row, min(j + 1, jlast));
+  float r2 = ld_depth<CLEAN>(row, min(j + 2, jlast));
+#pragma unroll 2
+  for (; k < N; k += 2 * kNT) {
+    int jn = j + inc2j, remn = rem + inc2r;
+    if (remn >= den) { remn -= den; ++jn; }
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (k + 2 * kNT < N) {
+      n0 = ld_depth<CLEAN>(row, jn);
+      n1 = ld_depth<CLEAN>(row, min(jn + 1, jlast));
+      n2 = ld_depth<CLEAN>(row, min(jn + 2, jlast));
+    }
+    const int rem1 = rem + num;
+    const bool same = rem1 < den;                  // second output still between row[j] and row[j+1]
     const float a1 = same ? r0 : r1, b1 = same ? r1 : r2;
     float2 o;
     o.x = fmaf(interp_w((float)rem * invden, c), r1 - r0, r0);
-    o.y = fmaf(interp_w((float)rem1 * invden, c), b1 - a1, a1);
+    o.y = fmaf(interp_w((float)(same ? rem1 : rem1 - den) * invden, c), b1 - a1, a1);
     zv.st2(k, o);
-    j += inc2j; rem += inc2r;
-    if (rem >= den) { rem -= den; ++j; }
+    j = jn; rem = remn; r0 = n0; r1 = n1; r2 = n2;
   }
 }
 
@@ -141,9 +160,15 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
   const double q0 = FS.q0, scale = FS.scale;
   double acc = 0.0;
   if (P.n_poly == 0 && P.model_out == nullptr) {
-#pragma unroll 4
-    for (int j = tid; j < P.n_obs; j += kNT) {
-      const double pp = (__ldg(F.obs_q + j) - q0) * scale;
+    int j = tid;
+    double q = 0.0, is = 0.0, ot = 0.0;
+    if (j < P.n_obs) { q = __ldg(F.obs_q + j); is = __ldg(P.obs_inv_s + j); ot = __ldg(F.obs_otm1 + j); }
+#pragma unroll 2
+    for (; j < P.n_obs; j += kNT) {
+      const int jn = j + kNT;
+      double qn = 0.0, isn = 0.0, otn = 0.0;       // next pixel's constants, requested early
+      if (jn < P.n_obs) { qn = __ldg(F.obs_q + jn); isn = __ldg(P.obs_inv_s + jn); otn = __ldg(F.obs_otm1 + jn); }
+      const double pp = (q - q0) * scale;
       double r;
       if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
       else {
@@ -151,9 +176,10 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
         const float dl = (float)(pp - (double)k);
         const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
         const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
-        r = fma((double)d, __ldg(P.obs_inv_s + j), -__ldg(F.obs_otm1 + j));
+        r = fma((double)d, is, -ot);
       }
       acc = fma(r, r, acc);
+      q = qn; is = isn; ot = otn;
     }
   } else {
     for (int j = tid; j < P.n_obs; j += kNT) {
@@ -183,11 +209,12 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);
   float* zf = reinterpret_cast<float*>(smem_raw);
-  __shared__ PointSetup S;
-  __shared__ FastSetup FS;
+  __shared__ FastPoint SP;
   __shared__ double red[kNT / 32];
+  PointSetup& S = SP.S;
+  FastSetup& FS = SP.FS;
   const int tid = threadIdx.x;
-  const TwTab tw{P.tw, P.log2tw};
+  const TwTab tw{P.tw, P.log2tw, P.twpass};
   const double nan = CUDART_NAN;
   constexpr int N1 = 1 << LOG2N1;
   constexpr bool kSplit = LOG2N1 >= 16;
@@ -195,23 +222,13 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   float* gline = kSplit ? F.scratch + (size_t)blockIdx.x * (N1 / 2) : nullptr;
   const ZSmem zs{zf};
   const ZSplit zp{zf, gline, N1 / 2};
+  float* win = zf + (kSplit ? N1 / 2 : N1);               // rotation-table window behind the transform buffer
+  const FastPoint* points = reinterpret_cast<const FastPoint*>(F.points);
 
   for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
-    const double* th = P.theta + (long long)p * P.ld;
     float* row = P.flux + (long long)p * P.ldf;
-    if (tid == 0) {
-      tail_setup(P, th, S);
-      if (!S.bad && S.use_inst) {
-        const int nM = S.i1 - S.i0 + 1, N2 = 1 << S.log2N2;
-        FS.s_num = nM - 1; FS.s_den = N2 - 1;
-        const long long inc = 2LL * kNT * (nM - 1);
-        FS.s_incj = (int)(inc / (N2 - 1));
-        FS.s_incr = (int)(inc - (long long)FS.s_incj * (N2 - 1));
-        FS.s_invden = 1.0f / (float)(N2 - 1);
-        FS.scale = (double)(N2 - 1) / (double)(nM - 1);
-        FS.q0 = (double)S.i0 + S.lnD * F.inv_dlnw;
-      }
-    }
+    if (tid < (int)(sizeof(FastPoint) / 16))
+      reinterpret_cast<int4*>(&SP)[tid] = __ldg(reinterpret_cast<const int4*>(points + p) + tid);
     __syncthreads();
     if (S.bad) {
       if (P.model_out)
@@ -225,12 +242,21 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     // ---------------- stage 1: rotational broadening on the full emulator grid
     if (S.do_rot) {
       const int n = P.n;
-      RotH H{P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
+      // the table entries this point can touch: [0, vsini_scale * N1/2 + 3]; staged in shared
+      // memory when they fit (the barrier after the regrid below publishes them)
+      const double xt_max = S.vsini_scale * (double)(N1 >> 1);
+      const bool in_win = xt_max + 5.0 <= (double)min(F.win_floats, P.ntab + 3);
+      if (in_win) {
+        const int nwin = (int)xt_max + 5;
+        for (int i = tid; i < nwin; i += kNT) win[i] = __ldg(P.sbtab + i);
+      }
+      RotH H{in_win ? win : P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
       if constexpr (!kSplit) {
-        stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+        if (!(P.debug_skip & 4))
+          stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
         __syncthreads();
-        ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
-        regrid_back(row, zs, F, tid, n, N1);
+        if (!(P.debug_skip & 1)) ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
+        if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1);
       } else {
         stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
         __syncthreads();
@@ -256,10 +282,11 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
           acc = final_pass(P, F, S, FS, zp, tid, p, N2);
         }
       } else {
-        stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+        if (!(P.debug_skip & 4))
+          stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
         __syncthreads();
-        convolve_any<LOG2N1>(z, log2N2, tw, F.twc, H, tid);
-        acc = final_pass(P, F, S, FS, zs, tid, p, N2);
+        if (!(P.debug_skip & 2)) convolve_any<LOG2N1>(z, log2N2, tw, F.twc, H, tid);
+        if (!(P.debug_skip & 16)) acc = final_pass(P, F, S, FS, zs, tid, p, N2);
       }
     } else {
       // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289)
@@ -296,6 +323,30 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     }
     __syncthreads();
   }
+}
+
+// One thread per point: mask limits, transform sizes, Doppler factor, taper constant, and the
+// stage-2 / final regrid ratios (the serial prologue of the tail, done for the whole slab at once).
+__global__ void __launch_bounds__(64)
+tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.B) return;
+  FastPoint* out = reinterpret_cast<FastPoint*>(F.points) + p;
+  PointSetup S{};
+  FastSetup FS{};
+  tail_setup(P, P.theta + (long long)p * P.ld, S);
+  if (!S.bad && S.use_inst) {
+    const int nM = S.i1 - S.i0 + 1, N2 = 1 << S.log2N2;
+    FS.s_num = nM - 1; FS.s_den = N2 - 1;
+    const long long inc = 2LL * kNT * (nM - 1);
+    FS.s_incj = (int)(inc / (N2 - 1));
+    FS.s_incr = (int)(inc - (long long)FS.s_incj * (N2 - 1));
+    FS.s_invden = 1.0f / (float)(N2 - 1);
+    FS.scale = (double)(N2 - 1) / (double)(nM - 1);
+    FS.q0 = (double)S.i0 + S.lnD * F.inv_dlnw;
+  }
+  out->S = S;
+  out->FS = FS;
 }
 
 }  // namespace payne

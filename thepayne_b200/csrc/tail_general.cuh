@@ -35,7 +35,7 @@ tail_general_kernel(const __grid_constant__ TailParams P, const __grid_constant_
   __shared__ PointSetup S;
   __shared__ double red[kTailThreads / 32];
   const int tid = threadIdx.x;
-  const TwTab tw{P.tw, P.log2tw};
+  const TwTab tw{P.tw, P.log2tw, P.twpass};
   const double nan = CUDART_NAN;
 
   for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
