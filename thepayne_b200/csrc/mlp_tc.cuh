@@ -421,7 +421,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
     int acc = 0; uint32_t aph = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
-      if constexpr (EPI == 0) {
+      constexpr bool kRegEpi = (EPI == 1 && MODE == kModeX3);   // hidden layer, rows stay in registers
+      if constexpr (EPI == 0 || kRegEpi) {
         // bias (+shift) and scale of this tile's columns -> shared memory, before the accumulator
         // is awaited so the loads are off the critical path
         ptx::epi_bar_sync();                       // previous tile's readers are done
@@ -446,6 +447,55 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
           if constexpr (MODE == kModeX3) ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
           ptx::tmem_ld_wait();
           epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
+        }
+      } else if constexpr (kRegEpi) {
+        // Hidden layer: thread = row.  Its 32 accumulator columns never leave registers:
+        // sigmoid, three fixed-point slices, and per plane four 16-byte stores of 8 bf16 (each
+        // row's 64 bytes are contiguous, so the stores fill whole sectors without a transpose).
+        const int grow = row_base + lane;
+        const bool rowok = grow < G.M;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int col0 = n0 + ch * 32;
+          if (col0 >= G.N) break;
+          uint32_t v[32], c[32];
+          ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
+          ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
+          ptx::tmem_ld_wait();
+          const long long o = (long long)grow * G.ldc + col0;
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + ch * 32);
+          const float4* s4 = reinterpret_cast<const float4*>(sscale + ch * 32);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            __align__(16) __nv_bfloat16 q1[8], q2[8], q3[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 bb = b4[2 * g8 + h], sc = s4[2 * g8 + h];
+              const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 8 * g8 + 4 * h + e;
+                const float val = sigmoidf_exact(fmaf(__uint_as_float(v[j]) + __uint_as_float(c[j]), scv[e], bbv[e]));
+                x3_split_act(val, q1[4 * h + e], q2[4 * h + e], q3[4 * h + e]);
+              }
+            }
+            if (rowok) {
+              const int gc = col0 + 8 * g8;
+              if (gc + 8 <= G.N) {
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out0 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q1);
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out1 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q2);
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out2 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q3);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (gc + e < G.N) {
+                    ((__nv_bfloat16*)G.out0)[o + 8 * g8 + e] = q1[e];
+                    ((__nv_bfloat16*)G.out1)[o + 8 * g8 + e] = q2[e];
+                    ((__nv_bfloat16*)G.out2)[o + 8 * g8 + e] = q3[e];
+                  }
+              }
+            }
+          }
         }
       } else {
 #pragma unroll 1
@@ -687,6 +737,39 @@ __global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __
   p1[r * ldd + c] = a; p2[r * ldd + c] = b; p3[r * ldd + c] = d;
 }
 
+// Label encode + first layer + fixed-point slicing in one pass (parity mode): one warp per point.
+// Lane i < D_in encodes label i once (fp64, NNmodels.py:164-168) and the warp shares the result;
+// each lane then forms outputs h = lane, lane + 32, ... with the same fmaf order as
+// encode_layer1_kernel and writes the three bf16 planes that lin2 reads.
+__global__ void __launch_bounds__(256)
+encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __restrict__ x, long long ld,
+                        const float* __restrict__ W1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ p1,
+                        __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldp, int B) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= B) return;
+  float mine = 0.f;
+  if (lane < E.D_in) {
+    const double raw = E.col[lane] >= 0 ? x[(long long)p * ld + E.col[lane]] : E.fixed[lane];
+    const float x32 = (float)raw;                                   // predictspec.py:70
+    mine = (float)(((double)x32 - E.xmin[lane]) / (E.xmax[lane] - E.xmin[lane]) - E.offset);
+  }
+  float enc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) enc[i] = __shfl_sync(0xffffffffu, mine, i);
+  for (int h = lane; h < E.H1; h += 32) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < E.D_in) acc = fmaf(enc[i], __ldg(W1 + h * E.D_in + i), acc);
+    const float v = sigmoidf_exact(acc + __ldg(b1 + h));
+    __nv_bfloat16 a, b, c;
+    x3_split_act(v, a, b, c);
+    const long long o = (long long)p * ldp + h;
+    p1[o] = a; p2[o] = b; p3[o] = c;
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -894,7 +977,9 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
                               float bias_shift, int sm_count, cudaStream_t st, long long* launches) {
   const long long tot = (long long)nb * dims_out[0];
   const unsigned blocks = (unsigned)((tot + 255) / 256);
-  if (MODE == kModeX3)
+  if (h1 == nullptr)
+    --*launches;      // the caller already wrote the sliced planes of layer 1 (encode_layer1_x3_kernel)
+  else if (MODE == kModeX3)
     x3_split_kernel<<<blocks, 256, 0, st>>>(h1, dims_out[0], (__nv_bfloat16*)actA->plane[0],
                                             (__nv_bfloat16*)actA->plane[1], (__nv_bfloat16*)actA->plane[2],
                                             actA->ld, nb, dims_out[0]);

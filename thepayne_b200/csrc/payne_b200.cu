@@ -312,7 +312,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   for (int i = 0; i < PAYNE_MAX_POLY; ++i) T.poly_col[i] = c->lay.poly_col[i];
   T.n_labels = s->D_in;
   for (int i = 0; i < 8; ++i) { T.label_col[i] = E.col[i]; T.label_fixed[i] = E.fixed[i]; }
-  c->ldf = ((long long)n + 3) / 4 * 4;
+  c->ldf = ((long long)n + 2 + 3) / 4 * 4;   // two finite pad floats per row (read, never used: tail_fast.cuh regrid_in)
 
   // ---- analytic regrid constants for the fast tail, verified against the exact tables
   {
@@ -484,6 +484,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
   if (c->has_spec) {
     const long long hmax = (std::max({c->H[0], c->H[1], c->H[2]}) + 7) / 8 * 8;
     CU_TRY(cudaMalloc((void**)&c->flux, (size_t)rows * c->ldf * sizeof(float)));
+    CU_TRY(cudaMemset(c->flux, 0, (size_t)rows * c->ldf * sizeof(float)));   // the row padding stays zero
     CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
@@ -502,12 +503,17 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
             float* out, long long ldo, bool want_depth, int* is_depth, cudaStream_t st) {
   using namespace payne;
   const int prec = c->lay.precision;
-  {
+  const bool fused_split = (prec == PAYNE_PREC_PARITY);   // encode + lin1 + slicing in one kernel
+  if (fused_split) {
+    encode_layer1_x3_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(
+        E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
+        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb);
+  } else {
     const long long tot = (long long)nb * c->H[0];
     encode_layer1_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, x, ld, c->W[0], c->b[0], c->hA,
                                                                          c->H[0], nb);
-    c->launches++;
   }
+  c->launches++;
   *is_depth = 0;
   if (prec == PAYNE_PREC_SIMT_FP32) {
     float* cur = c->hA; float* nxt = c->hB;
@@ -525,7 +531,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
       c->launches++;
     }
   } else {
-    int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, c->hA, &c->actA, &c->actB, nb, out, ldo,
+    int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, fused_split ? nullptr : c->hA, &c->actA, &c->actB,
+                           nb, out, ldo,
                            want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches);
     *is_depth = want_depth ? 1 : 0;
     if (rc) return fail(rc, "tensor-core MLP path failed (precision " + std::to_string(prec) + ")");

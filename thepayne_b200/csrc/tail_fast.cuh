@@ -85,58 +85,72 @@ struct ZSplit {                      // first half in shared memory, second half
 
 // Regrid a line-depth row (global/L2) onto N uniform ln-lambda points in shared memory:
 // out[k] = np.interp at native position j0 + k*num/den (num <= den).  Each thread makes PAIRS of
-// adjacent outputs (three row loads for two outputs, one 8-byte smem store); the source index of
-// the very last output is clamped with min(), its weight is exactly 0 there.
+// adjacent outputs (three row loads for two outputs, one 8-byte smem store).  The very last
+// output sits exactly on row[jlast] (weight 0), so row[jlast+1], row[jlast+2] are read but never
+// contribute: rows carry two finite pad floats (ensure_workspace zero-fills them once).
+// Two pairs per trip: six loads in flight per thread.
 template <bool CLEAN, class ZV>
 __device__ __forceinline__ void regrid_in(const float* row, const ZV& zv, int tid, int N, int num, int den,
-                                          int j0, int jlast, float invden, float c, int inc2j, int inc2r) {
+                                          int j0, float invden, float c, int inc2j, int inc2r) {
   const long long v = 2LL * tid * num;
   int j = (int)(v / den);
   int rem = (int)(v - (long long)j * den);
-  j += j0;
-  int k = 2 * tid;
-  if (k >= N) return;
-  // the three row values of the NEXT pair are requested before the current pair is interpolated
-  float r0 = ld_depth<CLEAN>(row, j);
-  float r1 = ld_depth<CLEAN>(row, min(j + 1, jlast));
-  float r2 = ld_depth<CLEAN>(row, min(j + 2, jlast));
-#pragma unroll 2
-  for (; k < N; k += 2 * kNT) {
-    int jn = j + inc2j, remn = rem + inc2r;
-    if (remn >= den) { remn -= den; ++jn; }
-    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-    if (k + 2 * kNT < N) {
-      n0 = ld_depth<CLEAN>(row, jn);
-      n1 = ld_depth<CLEAN>(row, min(jn + 1, jlast));
-      n2 = ld_depth<CLEAN>(row, min(jn + 2, jlast));
+  const float* src = row + j0 + j;
+#pragma unroll 1
+  for (int k = 2 * tid; k < N; k += 4 * kNT) {
+    const int remA = rem;
+    const float a0 = ld_depth<CLEAN>(src, 0), a1 = ld_depth<CLEAN>(src, 1), a2 = ld_depth<CLEAN>(src, 2);
+    rem += inc2r;
+    int adv = inc2j;
+    if (rem >= den) { rem -= den; ++adv; }
+    src += adv;
+    const int remB = rem;
+    const bool second = (k + 2 * kNT < N);         // false only for transforms below 1024 samples
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (second) { b0 = ld_depth<CLEAN>(src, 0); b1 = ld_depth<CLEAN>(src, 1); b2 = ld_depth<CLEAN>(src, 2); }
+    rem += inc2r;
+    adv = inc2j;
+    if (rem >= den) { rem -= den; ++adv; }
+    src += adv;
+    {
+      const int rem1 = remA + num;
+      const bool same = rem1 < den;                // second output still between row[j] and row[j+1]
+      const float lo = same ? a0 : a1, hi = same ? a1 : a2;
+      float2 o;
+      o.x = fmaf(interp_w((float)remA * invden, c), a1 - a0, a0);
+      o.y = fmaf(interp_w((float)(same ? rem1 : rem1 - den) * invden, c), hi - lo, lo);
+      zv.st2(k, o);
     }
-    const int rem1 = rem + num;
-    const bool same = rem1 < den;                  // second output still between row[j] and row[j+1]
-    const float a1 = same ? r0 : r1, b1 = same ? r1 : r2;
-    float2 o;
-    o.x = fmaf(interp_w((float)rem * invden, c), r1 - r0, r0);
-    o.y = fmaf(interp_w((float)(same ? rem1 : rem1 - den) * invden, c), b1 - a1, a1);
-    zv.st2(k, o);
-    j = jn; rem = remn; r0 = n0; r1 = n1; r2 = n2;
+    if (second) {
+      const int rem1 = remB + num;
+      const bool same = rem1 < den;
+      const float lo = same ? b0 : b1, hi = same ? b1 : b2;
+      float2 o;
+      o.x = fmaf(interp_w((float)remB * invden, c), b1 - b0, b0);
+      o.y = fmaf(interp_w((float)(same ? rem1 : rem1 - den) * invden, c), hi - lo, lo);
+      zv.st2(k + 2 * kNT, o);
+    }
   }
 }
 
 // ---- per-stage building blocks, templated on the sample view -------------------------------
 template <class ZV>
 __device__ __forceinline__ void stage_regrid(const PointSetup& S, const float* row, const ZV& zv, int tid, int N,
-                                             int num, int den, int j0, int jlast, float invden, float c,
-                                             int incj, int incr) {
-  if (S.clean) regrid_in<true>(row, zv, tid, N, num, den, j0, jlast, invden, c, incj, incr);
-  else regrid_in<false>(row, zv, tid, N, num, den, j0, jlast, invden, c, incj, incr);
+                                             int num, int den, int j0, float invden, float c, int incj, int incr) {
+  if (S.clean) regrid_in<true>(row, zv, tid, N, num, den, j0, invden, c, incj, incr);
+  else regrid_in<false>(row, zv, tid, N, num, den, j0, invden, c, incj, incr);
 }
 
-// stage-1 output back onto the emulator grid (+ edge patch of predictspec.py:240-241)
+// stage-1 output back onto the emulator grid (+ edge patch of predictspec.py:240-241); only
+// pixels [ilo, ihi] are produced -- stage 2 reads nothing outside its mask
 template <class ZV>
-__device__ __forceinline__ void regrid_back(float* row, const ZV& zv, const FastGrid& F, int tid, int n, int N1) {
-  int k, rem;
-  divmod_init<int>(tid, F.b_num, F.b_den, k, rem);
+__device__ __forceinline__ void regrid_back(float* row, const ZV& zv, const FastGrid& F, int tid, int n, int N1,
+                                            int ilo, int ihi) {
+  const long long v0 = (long long)(ilo + tid) * F.b_num;
+  int k = (int)(v0 / F.b_den);
+  int rem = (int)(v0 - (long long)k * F.b_den);
 #pragma unroll 4
-  for (int i = tid; i < n; i += kNT) {
+  for (int i = ilo + tid; i <= ihi; i += kNT) {
     const float dl = (float)rem * F.b_invden;
     const float g0 = zv.ld(k), g1 = zv.ld(min(k + 1, N1 - 1));
     const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
@@ -251,17 +265,19 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
         for (int i = tid; i < nwin; i += kNT) win[i] = __ldg(P.sbtab + i);
       }
       RotH H{in_win ? win : P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
+      // pixels stage 2 will read: its mask [i0, i1] (one more on each side keeps the edge patch exact)
+      const int blo = S.use_inst ? max(S.i0 - 1, 0) : 0, bhi = S.use_inst ? min(S.i1 + 1, n - 1) : n - 1;
       if constexpr (!kSplit) {
-        if (!(P.debug_skip & 4))
-          stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+        if (!(P.debug_skip & (4 | 32)))
+          stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
         __syncthreads();
         if (!(P.debug_skip & 1)) ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
-        if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1);
+        if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1, blo, bhi);
       } else {
-        stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, n - 1, F.f_invden, F.c_native, F.f_incj, F.f_incr);
+        stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
         __syncthreads();
         ct_convolve_split<LOG2MH>(z, reinterpret_cast<float2*>(gline), tw, F.twc, H, tid);
-        regrid_back(row, zp, F, tid, n, N1);
+        regrid_back(row, zp, F, tid, n, N1, blo, bhi);
       }
       __syncthreads();
     }
@@ -270,20 +286,20 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     if (S.use_inst) {
       // ---------------- stage 2: mask, regrid, Gaussian broadening
       const int log2N2 = S.log2N2, N2 = 1 << log2N2;
-      const int i0 = S.i0, i1 = S.i1;
+      const int i0 = S.i0;
       GaussH H{S.taper_a, 2.0f / (float)N2};
       bool split2 = false;
       if constexpr (kSplit) split2 = (log2N2 == LOG2N1);
       if (split2) {
         if constexpr (kSplit) {
-          stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+          stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
           __syncthreads();
           ct_convolve_split<LOG2MH>(z, reinterpret_cast<float2*>(gline), tw, F.twc, H, tid);
           acc = final_pass(P, F, S, FS, zp, tid, p, N2);
         }
       } else {
-        if (!(P.debug_skip & 4))
-          stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, i1, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
+        if (!(P.debug_skip & (4 | 64)))
+          stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
         __syncthreads();
         if (!(P.debug_skip & 2)) convolve_any<LOG2N1>(z, log2N2, tw, F.twc, H, tid);
         if (!(P.debug_skip & 16)) acc = final_pass(P, F, S, FS, zs, tid, p, N2);
