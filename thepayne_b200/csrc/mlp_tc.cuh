@@ -286,6 +286,18 @@ struct TcMaps {
   CUtensorMap c;       // EPI 0: fp32 output [M, N] (pitch ldc), boxes of 32 x 32, 128B swizzle
 };
 
+// Tensor maps of one layer, reusable while the buffers stay put: encoding seven descriptors through
+// the driver costs several microseconds of host time per launch, which is what bounds the latency
+// of small batches.  The maps cover `rows` (the allocated row count), not the batch: rows past the
+// batch are computed on stale data and land in workspace rows nobody reads.
+struct TcMapCache {
+  TcMaps maps;
+  const void* a0 = nullptr; const void* out = nullptr;
+  long long rows = 0, lda = 0, ldc = 0;
+  int variant = -1;
+};
+
+
 struct TcGemmArgs {
   const float* bias;
   const float* wscale;  // X3: per output column power-of-two scale
@@ -887,18 +899,31 @@ inline bool tc_multicast_enabled() {
 
 template <int BN, int MODE, int EPI, int MC>
 inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
-                          void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+                          void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
+                          TcMapCache* cache = nullptr, long long map_rows = 0) {
   using Cfg = TcCfg<BN, MODE>;
   static_assert(Cfg::kStages >= 2, "ring too shallow");
-  TcMaps T;
-  for (int p = 0; p < Cfg::kPlanes; ++p) {
-    const void* wp = MODE == kModeX3 ? W.xplane[p] : W.plane[p];
-    if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, Cfg::kElemBytes)) return PAYNE_E_CUDA;
-    if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, MC ? BN / 2 : BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+  constexpr int kVariant = BN * 1000 + MODE * 100 + EPI * 10 + MC;
+  const long long mrows = (cache && map_rows >= M) ? map_rows : M;
+  TcMaps local;
+  TcMaps& T = cache ? cache->maps : local;
+  const bool hit = cache && cache->variant == kVariant && cache->a0 == A.plane[0] && cache->out == out0 &&
+                   cache->rows == mrows && cache->lda == A.ld && cache->ldc == ldc;
+  if (!hit) {
+    if (cache) cache->variant = -1;
+    for (int p = 0; p < Cfg::kPlanes; ++p) {
+      const void* wp = MODE == kModeX3 ? W.xplane[p] : W.plane[p];
+      if (make_tmap(&T.a[p], A.plane[p], mrows, K, A.ld, kBM, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+      if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, MC ? BN / 2 : BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
+    }
+    for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
+    if (EPI == 0) { if (int rc = make_tmap_out(&T.c, out0, mrows, W.N, ldc)) return rc; }
+    else T.c = T.a[0];
+    if (cache) {
+      cache->a0 = A.plane[0]; cache->out = out0; cache->rows = mrows; cache->lda = A.ld; cache->ldc = ldc;
+      cache->variant = kVariant;
+    }
   }
-  for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
-  if (EPI == 0) { if (int rc = make_tmap_out(&T.c, out0, M, W.N, ldc)) return rc; }
-  else T.c = T.a[0];
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -962,19 +987,23 @@ inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float
 
 template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
-                     void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st) {
+                     void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
+                     TcMapCache* cache = nullptr, long long map_rows = 0) {
   if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_enabled())
     return tc_launch_2sm(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st);
   // multicast pays when many row tiles share each weight tile (the wide last layer)
   if (EPI == 0 && BN >= 128 && M > kBM && tc_multicast_enabled())
-    return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st);
-  return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st);
+    return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
+                                            map_rows);
+  return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
+                                          map_rows);
 }
 
 template <int MODE>
 inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                               const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
-                              float bias_shift, int sm_count, cudaStream_t st, long long* launches) {
+                              float bias_shift, int sm_count, cudaStream_t st, long long* launches,
+                              TcMapCache* caches, long long out_rows) {
   const long long tot = (long long)nb * dims_out[0];
   const unsigned blocks = (unsigned)((tot + 255) / 256);
   if (h1 == nullptr)
@@ -991,13 +1020,13 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
   int rc = PAYNE_OK;
   for (int k = 1; k < 5 && !rc; ++k) {
     rc = tc_launch<64, MODE, 1>(*cur, dims_in[k], tcw[k], bias[k], nxt->plane[0], nxt->plane[1], nxt->plane[2],
-                                nxt->ld, 0.f, nb, sm_count, st);
+                                nxt->ld, 0.f, nb, sm_count, st, caches ? caches + k : nullptr, cur->rows);
     ++*launches;
     TcActs* t = cur; cur = nxt; nxt = t;
   }
   if (rc) return rc;
   rc = tc_launch<128, MODE, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, nullptr, ldo, bias_shift, nb,
-                               sm_count, st);
+                               sm_count, st, caches ? caches + 5 : nullptr, out_rows >= cur->rows ? cur->rows : 0);
   ++*launches;
   return rc;
 }
@@ -1006,19 +1035,20 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
 // last layer's bias (the likelihood path asks for line depth f - 1 with bias_shift = -1).
 inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                          const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
-                         float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches) {
+                         float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                         TcMapCache* caches = nullptr, long long out_rows = 0) {
   for (int k = 1; k < 6; ++k)
     if (!tcw[k].plane[0]) return PAYNE_E_UNSUPPORTED;
   switch (prec) {
     case PAYNE_PREC_PARITY:
       return tc_run_layers_mode<kModeX3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
-                                         sm_count, st, launches);
+                                         sm_count, st, launches, caches, out_rows);
     case PAYNE_PREC_3XTF32:
       return tc_run_layers_mode<kModeT3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
-                                         sm_count, st, launches);
+                                         sm_count, st, launches, caches, out_rows);
     case PAYNE_PREC_TF32:
       return tc_run_layers_mode<kModeT1>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
-                                         sm_count, st, launches);
+                                         sm_count, st, launches, caches, out_rows);
     default:
       return PAYNE_E_UNSUPPORTED;
   }

@@ -119,6 +119,9 @@ double rot_sb(double u) {
 struct PayneCtx {
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry
+  payne::TcMapCache mapc[6];       // tensor maps per layer, valid while the workspace stays put
+  cudaStream_t side = nullptr;     // per-point tail setup runs here, beside the emulator GEMMs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   PayneLayout lay{};
   // spectrum emulator
   bool has_spec = false;
@@ -533,7 +536,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
   } else {
     int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, fused_split ? nullptr : c->hA, &c->actA, &c->actB,
                            nb, out, ldo,
-                           want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches);
+                           want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches, c->mapc,
+                           out == c->flux ? c->actA.rows : 0);
     *is_depth = want_depth ? 1 : 0;
     if (rc) return fail(rc, "tensor-core MLP path failed (precision " + std::to_string(prec) + ")");
   }
@@ -559,7 +563,22 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       CU_TRY(cudaEventRecord(evs[0], st));
     }
     int is_depth = 0;
+    const bool fast_tail = c->has_spec && c->use_fast && c->allow_fast;
+    TailParams T = c->tail;
     if (c->has_spec) {
+      T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb;
+      T.chi2_sed = c->has_phot ? c->chi2_sed : nullptr;
+      T.lnl = lnl ? lnl + p0 : nullptr;
+      T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
+      T.status = c->status;
+      if (fast_tail) {
+        // per-point setup depends only on theta: fork it beside the emulator GEMMs, join before the tail
+        CU_TRY(cudaEventRecord(c->ev_fork, st));
+        CU_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        tail_setup_kernel<<<(nb + 63) / 64, 64, 0, c->side>>>(T, c->fast);
+        CU_TRY(cudaEventRecord(c->ev_join, c->side));
+        c->launches++;
+      }
       rc = run_mlp(c, c->enc, th, ld, nb, c->flux, c->ldf, true, &is_depth, st);
       if (rc) return rc;
     }
@@ -573,16 +592,10 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
     }
     if (c->timing) CU_TRY(cudaEventRecord(evs[2], st));
     if (c->has_spec) {
-      TailParams T = c->tail;
-      T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb; T.flux_is_depth = is_depth;
-      T.chi2_sed = c->has_phot ? c->chi2_sed : nullptr;
-      T.lnl = lnl ? lnl + p0 : nullptr;
-      T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
-      T.status = c->status;
-      if (c->use_fast && c->allow_fast && is_depth) {
+      T.flux_is_depth = is_depth;
+      if (fast_tail) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+      if (fast_tail && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
-        tail_setup_kernel<<<(nb + 63) / 64, 64, 0, st>>>(T, c->fast);
-        c->launches++;
         switch (T.log2N1) {
           case 10: tail_fast_kernel<10><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
           case 11: tail_fast_kernel<11><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
@@ -643,6 +656,10 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
   c->has_spec = layout->spec_bool != 0; c->has_phot = layout->phot_bool != 0;
   int rc = PAYNE_OK;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(PAYNE_E_CUDA, "stream");
+  if (!rc && (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess))
+    rc = fail(PAYNE_E_CUDA, "side stream");
   if (!rc && cudaMalloc((void**)&c->status, sizeof(int)) != cudaSuccess) rc = fail(PAYNE_E_NOMEM, "status");
   if (!rc) cudaMemset(c->status, 0, sizeof(int));
   if (!rc && c->has_spec) rc = build_spec(c, spec, obs);
@@ -666,6 +683,9 @@ void payne_ctx_destroy(PayneCtx* c) {
   if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
   for (auto& evs : c->pending) for (auto e : evs) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
