@@ -390,7 +390,8 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     int occ0 = 0;
     const bool ok0 = probe(c->tail_smem, &occ0);
     size_t win = 0;
-    if (ok0 && occ0 >= 1) {
+    const char* wenv = getenv("PAYNE_ROT_WINDOW");            // "0": keep the table in L1/L2 only
+    if (ok0 && occ0 >= 1 && !(wenv && wenv[0] == '0')) {
       for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)10240, (size_t)8192, (size_t)6144,
                           (size_t)4096, (size_t)2048}) {
         int o = 0;

@@ -176,12 +176,12 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
   if (P.n_poly == 0 && P.model_out == nullptr) {
     int j = tid;
     double q = 0.0, is = 0.0, ot = 0.0;
-    if (j < P.n_obs) { q = __ldg(F.obs_q + j); is = __ldg(P.obs_inv_s + j); ot = __ldg(F.obs_otm1 + j); }
+    if (j < P.n_obs) { q = __ldcg(F.obs_q + j); is = __ldcg(P.obs_inv_s + j); ot = __ldcg(F.obs_otm1 + j); }
 #pragma unroll 2
     for (; j < P.n_obs; j += kNT) {
       const int jn = j + kNT;
       double qn = 0.0, isn = 0.0, otn = 0.0;       // next pixel's constants, requested early
-      if (jn < P.n_obs) { qn = __ldg(F.obs_q + jn); isn = __ldg(P.obs_inv_s + jn); otn = __ldg(F.obs_otm1 + jn); }
+      if (jn < P.n_obs) { qn = __ldcg(F.obs_q + jn); isn = __ldcg(P.obs_inv_s + jn); otn = __ldcg(F.obs_otm1 + jn); }
       const double pp = (q - q0) * scale;
       double r;
       if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
