@@ -198,3 +198,26 @@ def test_reference_interface_mirrors():
                                 rad_vel=pd['Vrad'], rot_vel=pd['Vrot'], vmic=np.nan,
                                 inst_R=2.355 * pd['Inst_R'], outwave=cfg.obs_wave)
     assert np.max(np.abs(fs - fr) / np.abs(fr)) < 1e-6
+
+
+def test_likelihood_from_hdf5_paths(tmp_path):
+    """fitargs['specANNpath'] / ['photANNpath'] as the reference passes them: HDF5 files in the
+    trainer's layout, read without h5py (thepayne_b200/h5lite.py) -> same lnL as the golden rows."""
+    from thepayne_b200 import annio
+    from thepayne_b200.fitting.likelihood import likelihood
+    cfg, g = load_case('mini_joint')
+    sp = str(tmp_path / 'specANN.h5')
+    annio.save_specnet(sp, cfg.spec)
+    annio.save_photnet(str(tmp_path / 'phot'), cfg.phot, fmt='h5')
+    fitpars_all = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist',
+                   'log(A)', 'Av', 'Rv', 'CarbonScale'] + [p for p in cfg.fitpars_i if 'pc' in p]
+    flags = {p: (p in cfg.fitpars_i) for p in fitpars_all}
+    fitargs = {'obs_wave_fit': cfg.obs_wave, 'obs_flux_fit': cfg.obs_flux, 'obs_eflux_fit': cfg.obs_eflux,
+               'obs_phot': cfg.obs_phot, 'specANNpath': sp, 'photANNpath': str(tmp_path / 'phot') + '/',
+               'NNtype': 'LinNet', 'fixedpars': {}}
+    like = likelihood(fitargs, [fitpars_all, flags], cfg.runbools, precision='parity')
+    out = like.lnlike_batch(torch.from_numpy(g['theta']).cuda()).cpu().numpy()
+    ref = g['lnl']
+    ok = np.isfinite(ref)
+    assert ok.sum() >= 4 and np.array_equal(np.isnan(out), ~ok)
+    assert np.all(np.abs(out[ok] - ref[ok]) <= np.maximum(1e-3, 1e-8 * np.abs(ref[ok])))

@@ -4,9 +4,10 @@ The reference stores a trained spectrum ANN as HDF5 with datasets ``label_i, xmi
 wavelengths, resolution, model/lin{1..6}.{weight,bias}`` (Payne/train/trainspec.py:214-228,
 read by Payne/predict/predictspec.py:43-59 and Payne/train/NNmodels.py:44-89) and one
 ``nnMIST_{band}.h5`` per photometric band with ``model/lin{1,2,3}.*, xmin, xmax``
-(Payne/predict/photANN.py:60-80).  h5py is not available in every deployment image, so the
-same dataset names are also accepted from an ``.npz`` archive; ``convert_h5`` turns one into
-the other wherever h5py exists.
+(Payne/predict/photANN.py:60-80).  Those files are read with h5py when it is installed and
+with the pure-Python reader ``h5lite`` otherwise; the same dataset names are also accepted from
+an ``.npz`` archive (``convert_h5``).  ``save_specnet`` / ``save_photnet`` write ``.h5`` in the
+reference's layout when the path ends in ``.h5``.
 """
 from __future__ import annotations
 
@@ -23,9 +24,11 @@ def _open(path):
         return {k: z[k] for k in z.files}
     try:
         import h5py
-    except ImportError as e:   # pragma: no cover - depends on the image
-        raise IOError('reading %s needs h5py; convert it to .npz with thepayne_b200.annio.convert_h5 '
-                      'on a machine that has it' % path) from e
+    except ImportError:
+        # no libhdf5 in this image: the reference's files (h5py defaults) are within what the
+        # pure-Python reader understands; anything else raises a descriptive IOError
+        from . import h5lite
+        return h5lite.read(path)
     out = {}
     with h5py.File(path, 'r') as f:
         def visit(name, obj):
@@ -47,6 +50,9 @@ def save_specnet(path, net: SpecNet):
     for k in range(6):
         d['model/lin%d.weight' % (k + 1)] = net.weights[k]
         d['model/lin%d.bias' % (k + 1)] = net.biases[k]
+    if path.endswith('.h5'):
+        from . import h5lite
+        return h5lite.write(path, d, gzip=('lin',))      # trainflux.py:567-570 gzips every model tensor
     np.savez_compressed(path, **d)
 
 
@@ -60,9 +66,17 @@ def load_specnet(path) -> SpecNet:
                    resolution=float(np.asarray(d['resolution'], dtype=float)), inlabels=labels)
 
 
-def save_photnet(dirpath, net: PhotNet):
+def save_photnet(dirpath, net: PhotNet, fmt='npz'):
     os.makedirs(dirpath, exist_ok=True)
     for i, b in enumerate(net.bands):
+        if fmt == 'h5':
+            from . import h5lite
+            h5lite.write(os.path.join(dirpath, 'nnMIST_%s.h5' % b), {
+                'model/lin1.weight': net.w1[i], 'model/lin1.bias': net.b1[i],
+                'model/lin2.weight': net.w2[i], 'model/lin2.bias': net.b2[i],
+                'model/lin3.weight': net.w3[i], 'model/lin3.bias': net.b3[i],
+                'xmin': net.xmin, 'xmax': net.xmax}, gzip=('lin',))
+            continue
         np.savez_compressed(os.path.join(dirpath, 'nnMIST_%s.npz' % b), **{
             'model/lin1.weight': net.w1[i], 'model/lin1.bias': net.b1[i],
             'model/lin2.weight': net.w2[i], 'model/lin2.bias': net.b2[i],
