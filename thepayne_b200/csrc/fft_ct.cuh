@@ -214,17 +214,108 @@ __device__ __forceinline__ void ct_contiguous16(float2* z, int tid) {
   }
 }
 
+// passes 1.. of the forward transform and the contiguous pass (pass 0 done by the caller)
 template <int LOG2M>
-__device__ __forceinline__ void ct_fft_forward(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+__device__ __forceinline__ void ct_fft_forward_rest(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
   using P = CtPlan<LOG2M>;
   constexpr bool WL = CtLast<LOG2M>::kWarpLocal;
-  if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, false>(z, tw, tc, tid); if (WL && P::n == 1) __syncwarp(); else __syncthreads(); }
+  if constexpr (P::n > 0) { if (WL && P::n == 1) __syncwarp(); else __syncthreads(); }
   if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, false>(z, tw, tc, tid); if (WL && P::n == 2) __syncwarp(); else __syncthreads(); }
   if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, false>(z, tw, tc, tid); if (WL && P::n == 3) __syncwarp(); else __syncthreads(); }
   if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, false>(z, tw, tc, tid); if (WL && P::n == 4) __syncwarp(); else __syncthreads(); }
   ct_contiguous16<LOG2M, false>(z, tid);
   __syncthreads();
 }
+template <int LOG2M>
+__device__ __forceinline__ void ct_fft_forward(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  using P = CtPlan<LOG2M>;
+  if constexpr (P::n > 0) ct_strided_pass<LOG2M, 0, false>(z, tw, tc, tid);
+  ct_fft_forward_rest<LOG2M>(z, tw, tc, tid);
+}
+
+// First forward pass with its inputs interpolated on the fly from a global row: complex element idx
+// is the pair of real samples (2 idx, 2 idx + 1) of the regridded signal, sample k = np.interp at row
+// position k * num / den (see tail_fast.cuh regrid_in, whose arithmetic this repeats).  Fusing the
+// regrid into the pass saves one full write + read of the transform buffer and a block barrier, and
+// lets the interpolation arithmetic run under the pass's shared-memory time.  The row must carry two
+// finite pad floats behind its last used element; NaN samples read as 0 (nan_to_num in depth space).
+template <int LOG2M>
+__device__ __forceinline__ void ct_pass0_regrid(float2* z, const TwTab& tw, const TwConst& tc, int tid,
+                                                const float* __restrict__ row, int num, int den, float invden,
+                                                float c) {
+  using P = CtPlan<LOG2M>;
+  static_assert(P::n > 0, "needs a strided pass");
+  constexpr int LR = P::lr(0), R = 1 << LR, LOG2S = LOG2M - LR, S = 1 << LOG2S;
+  constexpr int NBF = 1 << (LOG2M - LR);
+  constexpr int NB = (NBF + kNT - 1) / kNT;
+  constexpr int SPAN = S > kNT ? S / kNT : 1;
+  static_assert(SPAN <= 4, "first pass too wide for the constant table");
+  static_assert(SPAN == 1 || (LOG2M >= 13 && LOG2M <= 14), "constant table covers log2M 13..14");
+  const int jb = tid & (S - 1);
+  float2 wb[R];
+  {
+    const float4* pt = reinterpret_cast<const float4*>(tw.pass[LOG2M] + CtTwLayout<LOG2M>::off(0) + (jb << LR));
+#pragma unroll
+    for (int q = 0; q < R; q += 2) {
+      const float4 u = __ldg(pt + (q >> 1));
+      wb[q] = make_float2(u.x, u.y);
+      wb[q + 1] = make_float2(u.z, u.w);
+    }
+  }
+  // row position of complex element tid, and the steps for +kNT and +S elements
+  const long long v0 = 2LL * tid * num;
+  int j = (int)(v0 / den);
+  int rem = (int)(v0 - (long long)j * den);
+  const long long vi = 2LL * kNT * num, vm = 2LL * S * num;
+  const int ij = (int)(vi / den), ir = (int)(vi - (long long)ij * den);
+  const int mj = (int)(vm / den), mr = (int)(vm - (long long)mj * den);
+#pragma unroll 1
+  for (int i = 0; i < NB; ++i) {
+    const int g = tid + kNT * i;
+    if (NBF % kNT != 0 && g >= NBF) break;
+    float2 v[R];
+    {
+      const float* src = row + j;
+      int rr = rem;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        float a0 = src[0], a1 = src[1], a2 = src[2];
+        if (a0 != a0) a0 = 0.f;
+        if (a1 != a1) a1 = 0.f;
+        if (a2 != a2) a2 = 0.f;
+        const int rem1 = rr + num;
+        const bool same = rem1 < den;              // second sample still between row[j] and row[j+1]
+        const float lo = same ? a0 : a1, hi = same ? a1 : a2;
+        const float d0 = (float)rr * invden, d1 = (float)(same ? rem1 : rem1 - den) * invden;
+        v[m].x = fmaf(fmaf(d0 * (d0 - 1.f), c, d0), a1 - a0, a0);
+        v[m].y = fmaf(fmaf(d1 * (d1 - 1.f), c, d1), hi - lo, lo);
+        rr += mr;
+        int adv = mj;
+        if (rr >= den) { rr -= den; ++adv; }
+        src += adv;
+      }
+    }
+    rem += ir;
+    j += ij;
+    if (rem >= den) { rem -= den; ++j; }
+    const int sbase = swz(g);
+    constexpr int kSet = LOG2M >= 13 ? LOG2M - 13 : 0;
+    const int ip = i % SPAN;
+    dftR<R, false>(v);
+#pragma unroll
+    for (int q = 1; q < R; ++q) {
+      float2 w = wb[q];
+      if (SPAN > 1 && ip != 0) w = cmul(w, tc.c[kSet][ip][q]);
+      v[q] = cmul(v[q], w);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (LOG2S >= 7) z[sbase + (m << LOG2S)] = v[m];
+      else z[swz(g + (m << LOG2S))] = v[m];
+    }
+  }
+}
+
 template <int LOG2M>
 __device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
   using P = CtPlan<LOG2M>;
@@ -392,6 +483,16 @@ __device__ __forceinline__ void ct_convolve_split(float2* z, float2* g, const Tw
     g[j] = a - b;
   }
   __syncthreads();
+}
+
+// ct_convolve with the regrid of the input row fused into the first pass (see ct_pass0_regrid)
+template <int LOG2M, class HF>
+__device__ __forceinline__ void ct_convolve_regrid(float2* z, const TwTab& tw, const TwConst& tc, const HF& H, int tid,
+                                                   const float* row, int num, int den, float invden, float c) {
+  ct_pass0_regrid<LOG2M>(z, tw, tc, tid, row, num, den, invden, c);
+  ct_fft_forward_rest<LOG2M>(z, tw, tc, tid);
+  ct_filter_pairs<LOG2M>(z, tw, H, tid);
+  ct_fft_inverse<LOG2M>(z, tw, tc, tid);
 }
 
 template <int LOG2M, class HF>

@@ -74,8 +74,8 @@ struct TailParams {
   double* model_out;        // [B, n_obs] or null
   int* status;              // device flag: bit0 = a point needed a larger FFT than the carve-out
   int B;
-  int debug_skip;           // profiling aid (fast tail): bit0/1 skip the stage-1/2 transforms, bit2 the
-                            // regrids in, bit3 the regrid back, bit4 the final pass; results are garbage
+  int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
+                            // bit3 the regrid back, bit4 the final pass; results are garbage
 };
 
 struct PointSetup {

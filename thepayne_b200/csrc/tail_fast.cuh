@@ -268,10 +268,9 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       // pixels stage 2 will read: its mask [i0, i1] (one more on each side keeps the edge patch exact)
       const int blo = S.use_inst ? max(S.i0 - 1, 0) : 0, bhi = S.use_inst ? min(S.i1 + 1, n - 1) : n - 1;
       if constexpr (!kSplit) {
-        if (!(P.debug_skip & (4 | 32)))
-          stage_regrid(S, row, zs, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
-        __syncthreads();
-        if (!(P.debug_skip & 1)) ct_convolve<LOG2N1 - 1>(z, tw, F.twc, H, tid);
+        // regrid fused into the first FFT pass (measured against the separate regrid: tail -5 %)
+        if (!(P.debug_skip & 1))
+          ct_convolve_regrid<LOG2N1 - 1>(z, tw, F.twc, H, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native);
         if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1, blo, bhi);
       } else {
         stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
@@ -298,10 +297,23 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
           acc = final_pass(P, F, S, FS, zp, tid, p, N2);
         }
       } else {
-        if (!(P.debug_skip & (4 | 64)))
+        constexpr int LA = LOG2N1 > 15 ? 15 : LOG2N1;       // largest all-in-smem transform
+        if (!(log2N2 == LA || (LA >= 10 && log2N2 == LA - 1))) {
+          // small masks: separate regrid, runtime-planned transform
           stage_regrid(S, row, zs, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
-        __syncthreads();
-        if (!(P.debug_skip & 2)) convolve_any<LOG2N1>(z, log2N2, tw, F.twc, H, tid);
+          __syncthreads();
+          const Twiddles twr{tw.tab, tw.log2n};
+          FftPlan plan; plan.make(log2N2 - 1);
+          fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
+          filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
+          fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
+        } else if (!(P.debug_skip & 2)) {
+          if (log2N2 == LA)
+            ct_convolve_regrid<LA - 1>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den, FS.s_invden, F.c_native);
+          else
+            ct_convolve_regrid<(LA >= 10 ? LA - 2 : 8)>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den,
+                                                         FS.s_invden, F.c_native);
+        }
         if (!(P.debug_skip & 16)) acc = final_pass(P, F, S, FS, zs, tid, p, N2);
       }
     } else {

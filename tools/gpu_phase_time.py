@@ -23,8 +23,8 @@ def tail_ms(B, mask, n=10):
 
 grid = eng.query('tail_grid')
 print('tail grid', grid)
-for name, mask in [('full', 0), ('no fft1', 1), ('no fft2', 2), ('no ffts', 3), ('no regrid_in', 4), ('no regrid_in 1', 32), ('no regrid_in 2', 64), ('no regrid_back', 8),
-                   ('no final', 16), ('no regrids+final', 28), ('only ffts', 28), ('nothing', 31)]:
+for name, mask in [('full', 0), ('no stage 1', 1), ('no stage 2', 2), ('no stages', 3), ('no regrid_back', 8),
+                   ('no final', 16), ('only stages', 24), ('nothing', 27)]:
     print('%-18s %.4f ms' % (name, tail_ms(4096, mask)), flush=True)
 for B in [grid, 2 * grid, 9 * grid, 4096, 10 * grid]:
     ms = tail_ms(B, 0)
