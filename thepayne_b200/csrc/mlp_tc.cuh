@@ -769,16 +769,31 @@ encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __
   float enc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) enc[i] = __shfl_sync(0xffffffffu, mine, i);
-  for (int h = lane; h < E.H1; h += 32) {
-    float acc = 0.f;
+  // four outputs per trip so that their weight loads are in flight together (the kernel is a
+  // chain of L2 latencies otherwise)
+  for (int h0 = lane; h0 < E.H1; h0 += 128) {
+    float w[4][8], bb[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < E.D_in) acc = fmaf(enc[i], __ldg(W1 + h * E.D_in + i), acc);
-    const float v = sigmoidf_exact(acc + __ldg(b1 + h));
-    __nv_bfloat16 a, b, c;
-    x3_split_act(v, a, b, c);
-    const long long o = (long long)p * ldp + h;
-    p1[o] = a; p2[o] = b; p3[o] = c;
+    for (int u = 0; u < 4; ++u) {
+      const int h = h0 + 32 * u;
+      bb[u] = h < E.H1 ? __ldg(b1 + h) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[u][i] = (h < E.H1 && i < E.D_in) ? __ldg(W1 + h * E.D_in + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int h = h0 + 32 * u;
+      if (h >= E.H1) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < E.D_in) acc = fmaf(enc[i], w[u][i], acc);
+      const float v = sigmoidf_exact(acc + bb[u]);
+      __nv_bfloat16 a, b, c;
+      x3_split_act(v, a, b, c);
+      const long long o = (long long)p * ldp + h;
+      p1[o] = a; p2[o] = b; p3[o] = c;
+    }
   }
 }
 
