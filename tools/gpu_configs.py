@@ -1,5 +1,5 @@
 """Run the other BASELINE configs through the engine (dev tool): C3 joint spec+phot at 16k points,
-C5-sized slab run (131072 points on one GPU)."""
+C5-sized slab run (131072 points on one GPU), C4 monolithic (65536-point split transforms)."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,3 +28,4 @@ def run(name, B, ncheck=6):
 
 run('c3', 16384)
 run('c2', 131072)
+run('c4m', 4096, ncheck=3)
