@@ -221,3 +221,43 @@ def test_likelihood_from_hdf5_paths(tmp_path):
     ok = np.isfinite(ref)
     assert ok.sum() >= 4 and np.array_equal(np.isnan(out), ~ok)
     assert np.all(np.abs(out[ok] - ref[ok]) <= np.maximum(1e-3, 1e-8 * np.abs(ref[ok])))
+
+
+def test_rotation_kernel_paths_vs_oracle():
+    """Vrot from tiny to beyond the tabulated range: the shared-memory slice of the sb(u) table, the
+    global table (slice too large for the window) and the closed-form evaluation past the table end
+    all have to agree with the oracle (smoothing.py:610-629)."""
+    cfg, g = load_case('mini_spec')
+    eng = _engine(cfg, 'parity')
+    iv = cfg.fitpars_i.index('Vrot')
+    th = np.repeat(g['theta'][:1], 6, axis=0)
+    th[:, iv] = [0.05, 2.0, 40.0, 250.0, 700.0, -15.0]        # negative: sigma = sqrt(vsini^2) (smoothing.py:297)
+    flux, _, lnl = eng.model_batch(torch.from_numpy(np.ascontiguousarray(th)).cuda())
+    L = O.OracleLikelihood(cfg)
+    ref_l, ref_f, _ = L.lnlike_batch(th, return_model=True)
+    f = flux.cpu().numpy()
+    assert np.isfinite(ref_f).all()
+    assert np.max(np.abs(f - ref_f) / np.abs(ref_f)) < 1e-5
+    assert np.all(np.abs(lnl.cpu().numpy() - ref_l) <= np.maximum(1e-3, 1e-8 * np.abs(ref_l)))
+    assert eng.query('status') == 0
+    eng.close()
+
+
+def test_empty_batch_and_bad_arguments():
+    from thepayne_b200._lib import PayneError
+    cfg, g = load_case('mini_spec')
+    eng = _engine(cfg, 'parity')
+    out = eng.lnlike_batch(torch.zeros((0, cfg.ndim), dtype=torch.float64, device='cuda'))
+    assert out.shape == (0,)
+    assert eng.lnlike_batch(np.zeros((0, cfg.ndim))).shape == (0,)
+    with pytest.raises((PayneError, ValueError)):
+        eng.lnlike_batch(torch.zeros((3, cfg.ndim - 1), dtype=torch.float64, device='cuda'))
+    # the tensor-core emulator writes its output with TMA stores: the C ABI rejects a pitch that is
+    # not a multiple of 4 floats (and says why) instead of faulting
+    x = torch.zeros((2, eng.D_in), dtype=torch.float64, device='cuda')
+    ldy = (eng.D_out + 3) // 4 * 4 + 1
+    y = torch.empty((2, ldy), dtype=torch.float32, device='cuda')
+    rc = eng.lib.payne_ann_eval(eng._ctx, x.data_ptr(), 2, y.data_ptr(), ldy, None)
+    assert rc != 0 and b'multiple of 4' in eng.lib.payne_last_error()
+    assert eng.ann_eval(x).shape == (2, eng.D_out)            # the engine pads the pitch itself
+    eng.close()

@@ -692,18 +692,24 @@ void payne_ctx_destroy(PayneCtx* c) {
 
 int payne_lnlike_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t ld, double* lnl_dev,
                        void* stream) {
-  if (!c || !theta_dev || !lnl_dev) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c) return fail(PAYNE_E_INVALID, "null argument");
+  if (B == 0) return PAYNE_OK;                       // an empty batch may come with null buffers
+  if (!theta_dev || !lnl_dev) return fail(PAYNE_E_INVALID, "null argument");
   return run_batch(c, theta_dev, B, ld, nullptr, nullptr, lnl_dev, (cudaStream_t)stream);
 }
 
 int payne_model_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t ld, double* flux_dev,
                       double* mags_dev, double* lnl_dev, void* stream) {
-  if (!c || !theta_dev) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c) return fail(PAYNE_E_INVALID, "null argument");
+  if (B == 0) return PAYNE_OK;
+  if (!theta_dev) return fail(PAYNE_E_INVALID, "null argument");
   return run_batch(c, theta_dev, B, ld, flux_dev, mags_dev, lnl_dev, (cudaStream_t)stream);
 }
 
 int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, int64_t ld, double* lnl_host) {
-  if (!c || !theta_host || !lnl_host) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c) return fail(PAYNE_E_INVALID, "null argument");
+  if (B == 0) return PAYNE_OK;
+  if (!theta_host || !lnl_host) return fail(PAYNE_E_INVALID, "null argument");
   if (B <= 0) return PAYNE_OK;
   CU_TRY(cudaSetDevice(c->device));
   if (B > c->stage_cap || ld != c->stage_ld) {
@@ -731,7 +737,9 @@ int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, in
 }
 
 int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, int64_t ldy, void* stream) {
-  if (!c || !x_dev || !y_dev) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c) return fail(PAYNE_E_INVALID, "null argument");
+  if (B == 0) return PAYNE_OK;
+  if (!x_dev || !y_dev) return fail(PAYNE_E_INVALID, "null argument");
   if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
   if (ldy < c->D_out) return fail(PAYNE_E_INVALID, "ldy < D_out");
   if (c->lay.precision != PAYNE_PREC_SIMT_FP32 && ((ldy & 3) || ((uintptr_t)y_dev & 15)))
