@@ -145,9 +145,14 @@ int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, 
                    void* stream);
 
 /* Introspection for benches/tests: key is one of "n_ann","n_obs","nfft1","launches",
- * "grid_loguniform","max_batch","sm_count". Returns the value or -1. */
+ * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","status"
+ * (bit0: a point needed a larger transform than the shared-memory carve-out). Returns the value or -1. */
 int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
-/* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points). */
+/* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points), "timing" (0/1,
+ * see payne_ctx_last_ms), "fast_tail" (0 forces the general-grid tail), "debug_skip" (profiling aid:
+ * switches phases of the fused tail off, results are then meaningless; see csrc/tail.cuh).
+ * Environment, read once: PAYNE_ROT_WINDOW=0 (no shared-memory slice of the rotation-kernel table),
+ * PAYNE_GEMM_MULTICAST=1 / PAYNE_GEMM_2SM=1 (experimental GEMM variants, slower or equal). */
 int payne_ctx_set(PayneCtx* ctx, const char* key, int64_t value);
 
 /* Kernel unit-test hook: C[M,N] = A[M,K] . W[N,K]^T + bias[N] through the tensor-core GEMM of

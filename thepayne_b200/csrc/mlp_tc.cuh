@@ -902,10 +902,12 @@ inline void tc_free_acts(TcActs* a) {
   a->rows = 0;
 }
 
-// PAYNE_GEMM_MULTICAST=1 enables the 2-CTA weight multicast for the lin6 GEMM.  Measured on B200
-// (C2, B=4096): 0.330 ms vs 0.334 ms without -- no gain, because the bound is each SM's inbound
-// operand bandwidth (96 KB per 1536 MMA-cycles) and the 2-deep ring, neither of which multicast
-// changes; it only removes L2 reads.  Kept (tested) as the stepping stone to cta_group::2 tiles.
+// PAYNE_GEMM_MULTICAST=1 enables the 2-CTA weight multicast for the lin6 GEMM (each CTA of a pair
+// loads half of the weight tile and TMA-multicasts it to both).  Measured on B200 (C2, B=4096) it
+// removes 25 % of the L2 reads and changes the time by < 1 %: the kernel was never short of operand
+// bandwidth -- ncu's source view put ~75 % of its instructions in the old row-loop epilogue, and the
+// TMA-store epilogue (not multicast) is what lifted the tensor pipe from 40 % to 73 %.  Kept, tested,
+// off by default.
 inline bool tc_multicast_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("PAYNE_GEMM_MULTICAST"); v = (e && e[0] == '1') ? 1 : 0; }
