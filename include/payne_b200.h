@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PAYNE_ABI_VERSION 1
+#define PAYNE_ABI_VERSION 2
 
 enum {
   PAYNE_OK = 0,
@@ -74,8 +74,14 @@ enum {
   PAYNE_PREC_3XTF32 = 4
 };
 
-/* Spectrum emulator: LinNet (NNmodels.py:140-168); HOST pointers, copied at create.
- * W[k] is lin{k+1}.weight, row-major [out,in] fp32; b[k] is lin{k+1}.bias. */
+/* Spectrum emulator; HOST pointers, copied at create.  W[k] is layer k's weight, row-major
+ * [out,in] fp32; b[k] its bias.  Layer widths follow from n_layers:
+ *   6 (or 0): LinNet  D_in-H1-H1-H2-H2-H3-D_out, sigmoid          (NNmodels.py:140-168)
+ *   4       : SMLP    D_in-H1-H2-H3-D_out,      leaky ReLU 0.01   (NNmodels.py:92-115)
+ *   3       : YST1    D_in-H1-H2-D_out,         leaky ReLU 0.01   (predict/ystpred.py:18-58)
+ * The leaky-ReLU stacks run on the CUDA-core fp32 kernels whatever PayneLayout.precision says
+ * (the tensor-core operand slicing needs activations in [0,1)). */
+enum { PAYNE_ACT_SIGMOID = 0, PAYNE_ACT_LEAKY_RELU = 1 };
 typedef struct {
   int32_t D_in, H1, H2, H3, D_out;
   const float* W[6];
@@ -84,7 +90,11 @@ typedef struct {
   const double* xmax;        /* [D_in] */
   const double* wavelength;  /* [D_out], strictly increasing */
   double resolution;         /* sigma-R of the emulator grid (predictspec.py:49) */
-  double encode_offset;      /* 0.5 for LinNet (NNmodels.py:166) */
+  double encode_offset;      /* 0.5 for every reference net (NNmodels.py:166, ystpred.py:49) */
+  int32_t n_layers;          /* 0 = 6 */
+  int32_t activation;        /* PAYNE_ACT_* ; must be LEAKY_RELU for 3/4 layers, SIGMOID for 6 */
+  int32_t label_fp32_cast;   /* 1: labels pass through fp32 first (ANN.eval, predictspec.py:70); 0: fp64 (ystpred.py:47-50) */
+  int32_t reserved_;
 } PayneSpecNet;
 
 /* Photometry emulator: stacked per-band Net(6,H,1) (photANN.py:97-106); HOST pointers. */

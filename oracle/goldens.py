@@ -31,6 +31,9 @@ CASES = {
     'c4m': (dict(kind='c4'), 8, 2),
     # awkward shapes: hidden width 100 (not a multiple of 8), odd pixel counts
     'mini_odd': (dict(kind='mini', H=100, ann_range=(5141.0, 5187.3), obs_range=(5150.0, 5180.0), n_obs=1501), 8, 8),
+    # legacy leaky-ReLU emulators: SMLP = torch fp32, 4 layers; YST1 = numpy fp64, 3 layers
+    'mini_smlp': (dict(kind='mini', nntype='SMLP'), 12, 12),
+    'mini_yst': (dict(kind='mini', nntype='YST1', H=48), 12, 12),
 }
 
 

@@ -66,6 +66,47 @@ class TorchLinNet:
         return y.numpy()          # [B, D_out] float32
 
 
+class LegacyNet:
+    """The two leaky-ReLU emulators the reference still accepts.
+
+    ``SMLP`` (``NNmodels.py:92-115``, driven by ``ANN.eval`` ``predictspec.py:61-74``): torch fp32,
+    ``Linear, LeakyReLU`` x3 + ``Linear``; encode in numpy on the FloatTensor's values.
+    ``YST1`` (``predict/ystpred.py:47-58``): numpy all the way -- float64 labels, the stored weight
+    arrays as they are, ``z*(z>0) + 0.01*z*(z<0)``, three ``einsum`` layers."""
+
+    def __init__(self, spec):
+        self.spec = spec
+
+    def __call__(self, x):
+        sp = self.spec
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        if sp.nntype == 'SMLP':
+            x32 = torch.from_numpy(x).type(torch.FloatTensor)
+            enc = (x32.numpy() - sp.xmin) / (sp.xmax - sp.xmin) - 0.5
+            h = torch.from_numpy(enc).type(torch.FloatTensor)
+            W = [torch.from_numpy(np.ascontiguousarray(w)) for w in sp.weights]
+            b = [torch.from_numpy(np.ascontiguousarray(v)) for v in sp.biases]
+            with torch.no_grad():
+                for k in range(3):
+                    h = torch.nn.functional.leaky_relu(torch.nn.functional.linear(h, W[k], b[k]))
+                y = torch.nn.functional.linear(h, W[3], b[3])
+            return y.numpy()
+        lrelu = lambda z: z * (z > 0) + 0.01 * z * (z < 0)
+        out = []
+        for row in x:
+            xi = (row - sp.xmin) / (sp.xmax - sp.xmin) - 0.5
+            inside = np.einsum('ij,j->i', sp.weights[0], xi) + sp.biases[0]
+            outside = np.einsum('ij,j->i', sp.weights[1], lrelu(inside)) + sp.biases[1]
+            out.append(np.einsum('ij,j->i', sp.weights[2], lrelu(outside)) + sp.biases[2])
+        return np.array(out)      # [B, D_out] float64
+
+
+def make_net(spec, ideal=False):
+    return TorchLinNet(spec, ideal=ideal) if spec.nntype == 'LinNet' else LegacyNet(spec)
+
+
 # --------------------------------------------------------------------------- smoothing
 def _resample_pow2(w, s):
     """``smoothing.py:649-668`` resample_wave (log branch)."""
@@ -218,7 +259,7 @@ class OracleLikelihood:
         self.fitpars_i = list(cfg.fitpars_i)
         self.ndim = len(self.fitpars_i)
         self.fixedpars = dict(cfg.fixedpars)
-        self.net = TorchLinNet(cfg.spec, ideal=ideal_mlp) if self.spec_bool else None
+        self.net = make_net(cfg.spec, ideal=ideal_mlp) if self.spec_bool else None
         self.parsdict = {}
 
     # likelihood.py:42-82

@@ -77,7 +77,7 @@ def load():
     for short, full in [('smoothing', 'Payne.utils.smoothing'), ('NNmodels', 'Payne.train.NNmodels'),
                         ('predictspec', 'Payne.predict.predictspec'), ('photANN', 'Payne.predict.photANN'),
                         ('highred', 'Payne.predict.highred'), ('predictsed', 'Payne.predict.predictsed'),
-                        ('fitutils', 'Payne.fitting.fitutils'), ('genmod', 'Payne.fitting.genmod'),
+                        ('ystpred', 'Payne.predict.ystpred'), ('fitutils', 'Payne.fitting.fitutils'), ('genmod', 'Payne.fitting.genmod'),
                         ('likelihood', 'Payne.fitting.likelihood'), ('prior', 'Payne.fitting.prior')]:
         setattr(ns, short, importlib.import_module(full))
     _mods = ns
@@ -99,22 +99,43 @@ def build_likelihood(cfg):
     like.ndim = len(like.fitpars_i)
     GM = R.genmod.GenMod()
     like.GM = GM
-    if like.spec_bool:
-        H1, H2, H3 = s.weights[0].shape[0], s.weights[3].shape[0], s.weights[4].shape[0]
-        model = R.NNmodels.LinNet(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
-        sd = {}
-        for k in range(6):
-            sd['lin%d.weight' % (k + 1)] = torch.from_numpy(s.weights[k].copy())
-            sd['lin%d.bias' % (k + 1)] = torch.from_numpy(s.biases[k].copy())
+    if like.spec_bool and getattr(s, 'nntype', 'LinNet') == 'YST1':
+        # ystpred.Net holds plain arrays (ystpred.py:25-37); PayneSpecPredict as GenMod builds it for
+        # NNtype='YST1' (genmod.py:18-21)
+        net = R.ystpred.Net.__new__(R.ystpred.Net)
+        net.w_array_0, net.w_array_1, net.w_array_2 = [w.copy() for w in s.weights]
+        net.b_array_0, net.b_array_1, net.b_array_2 = [b.copy() for b in s.biases]
+        net.xmin, net.xmax = s.xmin.copy(), s.xmax.copy()
+        net.wavelength = s.wavelength.copy()
+        net.resolution = float(s.resolution)
+        PP = R.ystpred.PayneSpecPredict.__new__(R.ystpred.PayneSpecPredict)
+        PP.anns, PP.Canns, PP.NN, PP.NNtype = net, None, {}, 'YST1'
+        GM.PP = PP
+    elif like.spec_bool:
+        nntype = getattr(s, 'nntype', 'LinNet')
+        if nntype == 'SMLP':
+            H1, H2, H3 = [w.shape[0] for w in s.weights[:3]]
+            model = R.NNmodels.SMLP(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
+            sd = {}
+            for k in range(4):
+                sd['features.%d.weight' % (2 * k)] = torch.from_numpy(s.weights[k].copy())
+                sd['features.%d.bias' % (2 * k)] = torch.from_numpy(s.biases[k].copy())
+        else:
+            H1, H2, H3 = s.weights[0].shape[0], s.weights[3].shape[0], s.weights[4].shape[0]
+            model = R.NNmodels.LinNet(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
+            sd = {}
+            for k in range(6):
+                sd['lin%d.weight' % (k + 1)] = torch.from_numpy(s.weights[k].copy())
+                sd['lin%d.bias' % (k + 1)] = torch.from_numpy(s.biases[k].copy())
         model.load_state_dict(sd)
         model.eval()
         model.D_in = s.D_in
         ann = R.predictspec.ANN.__new__(R.predictspec.ANN)
         ann.model, ann.wavelength = model, s.wavelength.copy()
         ann.resolution = np.array(s.resolution, dtype=float)
-        ann.xmin, ann.xmax, ann.inlabels, ann.NNtype = s.xmin, s.xmax, s.inlabels, 'LinNet'
+        ann.xmin, ann.xmax, ann.inlabels, ann.NNtype = s.xmin, s.xmax, s.inlabels, nntype
         PP = R.predictspec.PayneSpecPredict.__new__(R.predictspec.PayneSpecPredict)
-        PP.anns, PP.Canns, PP.NN, PP.NNtype = ann, None, {}, 'LinNet'
+        PP.anns, PP.Canns, PP.NN, PP.NNtype = ann, None, {}, nntype
         GM.PP = PP
     if like.phot_bool:
         p = cfg.phot

@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.payne_abi_version() == 1
+    assert lib.payne_abi_version() == 2
 
 
 def test_struct_layout_matches_header(lib, tmp_path):

@@ -261,3 +261,31 @@ def test_empty_batch_and_bad_arguments():
     assert rc != 0 and b'multiple of 4' in eng.lib.payne_last_error()
     assert eng.ann_eval(x).shape == (2, eng.D_out)            # the engine pads the pitch itself
     eng.close()
+
+
+@pytest.mark.parametrize('name,nntype', [('mini_smlp', 'SMLP'), ('mini_yst', 'YST1')])
+def test_legacy_nets_through_the_mirrors(tmp_path, name, nntype):
+    """the leaky-ReLU emulators (NNmodels.SMLP, ystpred.Net) through the drop-in
+    likelihood, selected by fitargs['NNtype'] like the reference (likelihood.py:28, genmod.py:18-21),
+    loaded from an HDF5 file in the reference's own layout."""
+    from thepayne_b200 import annio
+    from thepayne_b200.fitting.likelihood import likelihood
+    cfg, g = load_case(name)
+    path = str(tmp_path / 'net.h5')
+    annio.save_specnet(path, cfg.spec)
+    fitpars_all = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist',
+                   'log(A)', 'Av', 'Rv', 'CarbonScale']
+    flags = {p: (p in cfg.fitpars_i) for p in fitpars_all}
+    fitargs = {'obs_wave_fit': cfg.obs_wave, 'obs_flux_fit': cfg.obs_flux, 'obs_eflux_fit': cfg.obs_eflux,
+               'specANNpath': path, 'NNtype': nntype, 'fixedpars': {}}
+    like = likelihood(fitargs, [fitpars_all, flags], cfg.runbools)
+    assert type(like.GM.PP).__module__.endswith('ystpred' if nntype == 'YST1' else 'predictspec')
+    out = like.lnlike_batch(torch.from_numpy(g['theta']).cuda()).cpu().numpy()
+    ref = g['lnl']
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isnan(out), ~ok)
+    assert np.all(np.abs(out[ok] - ref[ok]) <= np.maximum(1e-3, 1e-8 * np.abs(ref[ok])))
+    # ANN.eval / Net.eval: the bare network against the oracle's restatement of it
+    y = like.GM.PP.anns.eval(list(g['theta'][0][:4]))
+    yo = O.make_net(cfg.spec)(g['theta'][0][:4])[0]
+    assert np.max(np.abs(y - yo)) < 2e-6

@@ -30,7 +30,9 @@ _d = C.POINTER(C.c_double)
 class PayneSpecNet(C.Structure):
     _fields_ = [('D_in', C.c_int32), ('H1', C.c_int32), ('H2', C.c_int32), ('H3', C.c_int32),
                 ('D_out', C.c_int32), ('W', _f * 6), ('b', _f * 6), ('xmin', _d), ('xmax', _d),
-                ('wavelength', _d), ('resolution', C.c_double), ('encode_offset', C.c_double)]
+                ('wavelength', _d), ('resolution', C.c_double), ('encode_offset', C.c_double),
+                ('n_layers', C.c_int32), ('activation', C.c_int32), ('label_fp32_cast', C.c_int32),
+                ('reserved_', C.c_int32)]
 
 
 class PaynePhotNet(C.Structure):

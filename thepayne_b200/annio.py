@@ -44,26 +44,51 @@ def convert_h5(src, dst):
     return dst
 
 
-def save_specnet(path, net: SpecNet):
+def _spec_datasets(net: SpecNet):
+    """Dataset names per network type, as the reference's trainers / readers use them."""
+    if net.nntype == 'YST1':                       # predict/ystpred.py:25-37
+        d = {'x_min': net.xmin, 'x_max': net.xmax, 'wavelength': net.wavelength,
+             'resolution': np.array([net.resolution])}
+        for k in range(3):
+            d['w_array_%d' % k] = net.weights[k]
+            d['b_array_%d' % k] = net.biases[k]
+        return d
     d = {'label_i': np.array([s.encode() for s in net.inlabels]), 'xmin': net.xmin, 'xmax': net.xmax,
          'wavelengths': net.wavelength, 'resolution': np.array(net.resolution)}
-    for k in range(6):
-        d['model/lin%d.weight' % (k + 1)] = net.weights[k]
-        d['model/lin%d.bias' % (k + 1)] = net.biases[k]
+    for k in range(net.n_layers):
+        name = 'model/lin%d' % (k + 1) if net.nntype == 'LinNet' else 'model/features.%d' % (2 * k)  # NNmodels.py:51-63
+        d[name + '.weight'] = net.weights[k]
+        d[name + '.bias'] = net.biases[k]
+    return d
+
+
+def save_specnet(path, net: SpecNet):
+    d = _spec_datasets(net)
     if path.endswith('.h5'):
         from . import h5lite
-        return h5lite.write(path, d, gzip=('lin',))      # trainflux.py:567-570 gzips every model tensor
+        return h5lite.write(path, d, gzip=('lin', 'features'))      # trainflux.py:567-570 gzips every model tensor
     np.savez_compressed(path, **d)
 
 
-def load_specnet(path) -> SpecNet:
+def load_specnet(path, NNtype=None) -> SpecNet:
+    """``NNtype`` None: inferred from the dataset names (LinNet ``model/lin*``, SMLP
+    ``model/features.*``, YST1 ``w_array_*``)."""
     d = _open(path)
+    if NNtype is None:
+        NNtype = 'YST1' if 'w_array_0' in d else ('SMLP' if 'model/features.0.weight' in d else 'LinNet')
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    if NNtype == 'YST1':
+        return SpecNet(weights=[f32(d['w_array_%d' % k]) for k in range(3)],
+                       biases=[f32(d['b_array_%d' % k]) for k in range(3)],
+                       xmin=f64(d['x_min']), xmax=f64(d['x_max']), wavelength=f64(d['wavelength']),
+                       resolution=float(np.asarray(d['resolution'], dtype=float).reshape(-1)[0]), nntype='YST1')
     labels = [x.decode('utf-8') if isinstance(x, bytes) else str(x) for x in d['label_i']]
-    return SpecNet(weights=[np.asarray(d['model/lin%d.weight' % k], dtype=np.float32) for k in range(1, 7)],
-                   biases=[np.asarray(d['model/lin%d.bias' % k], dtype=np.float32) for k in range(1, 7)],
-                   xmin=np.asarray(d['xmin'], dtype=np.float64), xmax=np.asarray(d['xmax'], dtype=np.float64),
-                   wavelength=np.asarray(d['wavelengths'], dtype=np.float64),
-                   resolution=float(np.asarray(d['resolution'], dtype=float)), inlabels=labels)
+    names = ['model/lin%d' % k for k in range(1, 7)] if NNtype == 'LinNet' else \
+        ['model/features.%d' % k for k in (0, 2, 4, 6)]
+    return SpecNet(weights=[f32(d[n + '.weight']) for n in names], biases=[f32(d[n + '.bias']) for n in names],
+                   xmin=f64(d['xmin']), xmax=f64(d['xmax']), wavelength=f64(d['wavelengths']),
+                   resolution=float(np.asarray(d['resolution'], dtype=float)), inlabels=labels, nntype=NNtype)
 
 
 def save_photnet(dirpath, net: PhotNet, fmt='npz'):

@@ -11,6 +11,15 @@
 namespace payne {
 
 __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+// LeakyReLU(0.01): torch's (NNmodels.py:101) and the numpy z*(z>0)+0.01*z*(z<0) of ystpred.py:41-45
+__device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }
+constexpr int kActNone = 0, kActSigmoid = 1, kActLeaky = 2;
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if (ACT == kActSigmoid) return sigmoidf_exact(v);
+  if (ACT == kActLeaky) return leaky_relu(v);
+  return v;
+}
 
 struct EncodeParams {
   int D_in, H1;
@@ -18,6 +27,8 @@ struct EncodeParams {
   double fixed[8];
   double xmin[8], xmax[8];
   double offset;
+  int cast32;        // labels through fp32 first (predictspec.py:70); 0 for the fp64 YST1 path
+  int act;           // kActSigmoid / kActLeaky for the first layer
 };
 
 // h1[p, h] = sigmoid(W1[h, :] . enc(x_p) + b1[h]); optionally also the tf32 hi/lo split planes.
@@ -32,15 +43,16 @@ encode_layer1_kernel(const __grid_constant__ EncodeParams E, const double* __res
   float acc = 0.f;
   for (int i = 0; i < E.D_in; ++i) {
     const double raw = E.col[i] >= 0 ? x[(long long)p * ld + E.col[i]] : E.fixed[i];
-    const float x32 = (float)raw;                                   // predictspec.py:70
-    const float enc = (float)(((double)x32 - E.xmin[i]) / (E.xmax[i] - E.xmin[i]) - E.offset);
+    const double x = E.cast32 ? (double)(float)raw : raw;            // predictspec.py:70
+    const float enc = (float)((x - E.xmin[i]) / (E.xmax[i] - E.xmin[i]) - E.offset);
     acc = fmaf(enc, __ldg(W1 + h * E.D_in + i), acc);
   }
-  out[(long long)p * ldo + h] = sigmoidf_exact(acc + __ldg(b1 + h));
+  const float v = acc + __ldg(b1 + h);
+  out[(long long)p * ldo + h] = E.act == kActLeaky ? leaky_relu(v) : sigmoidf_exact(v);
 }
 
 // C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]); all row-major; fp32 FMA accumulation.
-template <bool SIGMOID>
+template <int ACT>
 __global__ void __launch_bounds__(256)
 sgemm_bias_act_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W,
                       const float* __restrict__ bias, float* __restrict__ C, long long ldc,
@@ -87,7 +99,7 @@ sgemm_bias_act_kernel(const float* __restrict__ A, long long lda, const float* _
       const int gn = n0 + tx * 8 + j;
       if (gn >= N) continue;
       float v = acc[i][j] + (__ldg(bias + gn) + bias_shift);
-      if (SIGMOID) v = sigmoidf_exact(v);
+      v = activate<ACT>(v);
       C[(long long)gm * ldc + gn] = v;
     }
   }

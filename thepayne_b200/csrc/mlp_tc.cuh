@@ -763,8 +763,8 @@ encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __
   float mine = 0.f;
   if (lane < E.D_in) {
     const double raw = E.col[lane] >= 0 ? x[(long long)p * ld + E.col[lane]] : E.fixed[lane];
-    const float x32 = (float)raw;                                   // predictspec.py:70
-    mine = (float)(((double)x32 - E.xmin[lane]) / (E.xmax[lane] - E.xmin[lane]) - E.offset);
+    const double xv = E.cast32 ? (double)(float)raw : raw;          // predictspec.py:70
+    mine = (float)((xv - E.xmin[lane]) / (E.xmax[lane] - E.xmin[lane]) - E.offset);
   }
   float enc[8];
 #pragma unroll

@@ -119,6 +119,8 @@ double rot_sb(double u) {
 struct PayneCtx {
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry
+  int n_layers = 6;
+  bool legacy = false;             // leaky-ReLU stack (SMLP / YST1): CUDA-core fp32 layers only
   payne::TcMapCache mapc[6];       // tensor maps per layer, valid while the workspace stays put
   cudaStream_t side = nullptr;     // per-point tail setup runs here, beside the emulator GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -177,9 +179,22 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   c->D_in = s->D_in; c->H[0] = s->H1; c->H[1] = s->H2; c->H[2] = s->H3; c->D_out = s->D_out;
   if (s->D_in < 1 || s->D_in > 8) return fail(PAYNE_E_INVALID, "D_in must be in [1,8]");
   if (s->D_out < 32) return fail(PAYNE_E_INVALID, "D_out must be >= 32");
-  const int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
-  const int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
-  for (int k = 0; k < 6; ++k) {
+  const int nl = s->n_layers == 0 ? 6 : s->n_layers;
+  if (nl != 6 && nl != 4 && nl != 3) return fail(PAYNE_E_INVALID, "n_layers must be 6 (LinNet), 4 (SMLP) or 3 (YST1)");
+  if ((nl == 6) != (s->activation == PAYNE_ACT_SIGMOID))
+    return fail(PAYNE_E_UNSUPPORTED, "supported emulators: 6 sigmoid layers, or 3/4 leaky-ReLU layers");
+  c->n_layers = nl;
+  c->legacy = (nl != 6);
+  int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
+  int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
+  if (nl == 4) {                                   // NNmodels.py:99-107
+    const int a[4] = {s->D_in, s->H1, s->H2, s->H3}, b[4] = {s->H1, s->H2, s->H3, s->D_out};
+    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  } else if (nl == 3) {                            // ystpred.py:25-30
+    const int a[3] = {s->D_in, s->H1, s->H2}, b[3] = {s->H1, s->H2, s->D_out};
+    for (int k = 0; k < 3; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  }
+  for (int k = 0; k < nl; ++k) {
     c->dims_in[k] = din[k]; c->dims_out[k] = dout[k];
     int rc = upload_owned(c, &c->W[k], s->W[k], (size_t)din[k] * dout[k]);
     if (rc) return rc;
@@ -188,6 +203,8 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   }
   EncodeParams& E = c->enc;
   E.D_in = s->D_in; E.H1 = s->H1; E.offset = s->encode_offset;
+  E.cast32 = (nl == 6) ? 1 : (s->label_fp32_cast != 0);
+  E.act = c->legacy ? kActLeaky : kActSigmoid;
   const int label_par[5] = {PAYNE_P_TEFF, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VMIC};
   for (int i = 0; i < 8; ++i) {
     E.col[i] = -1; E.fixed[i] = std::numeric_limits<double>::quiet_NaN(); E.xmin[i] = 0; E.xmax[i] = 1;
@@ -433,8 +450,8 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     return fail(PAYNE_E_UNSUPPORTED,
                 "a 65536-point transform needs the log-uniform fast tail (emulator grid is not log-uniform)");
   }
-  // tensor-core operand copies of the weights
-  for (int k = 1; k < 6; ++k) {
+  // tensor-core operand copies of the weights (sigmoid LinNet only)
+  for (int k = 1; k < 6 && !c->legacy; ++k) {
     rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
     if (rc) return fail(rc, "tc_prepare_weights failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
   }
@@ -507,7 +524,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
             float* out, long long ldo, bool want_depth, int* is_depth, cudaStream_t st) {
   using namespace payne;
   const int prec = c->lay.precision;
-  const bool fused_split = (prec == PAYNE_PREC_PARITY);   // encode + lin1 + slicing in one kernel
+  const bool simt = c->legacy || prec == PAYNE_PREC_SIMT_FP32;
+  const bool fused_split = !simt && (prec == PAYNE_PREC_PARITY);   // encode + lin1 + slicing in one kernel
   if (fused_split) {
     encode_layer1_x3_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(
         E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
@@ -519,17 +537,21 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
   }
   c->launches++;
   *is_depth = 0;
-  if (prec == PAYNE_PREC_SIMT_FP32) {
+  if (simt) {
     float* cur = c->hA; float* nxt = c->hB;
-    for (int k = 1; k < 6; ++k) {
+    const int nl = c->n_layers;
+    for (int k = 1; k < nl; ++k) {
       const int K = c->dims_in[k], N = c->dims_out[k];
       dim3 grid((N + 127) / 128, (nb + 127) / 128);
-      if (k < 5) {
-        sgemm_bias_act_kernel<true><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K, 0.f);
+      if (k < nl - 1) {
+        if (c->legacy)
+          sgemm_bias_act_kernel<kActLeaky><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K, 0.f);
+        else
+          sgemm_bias_act_kernel<kActSigmoid><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K, 0.f);
         std::swap(cur, nxt);
       } else {
-        sgemm_bias_act_kernel<false><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K,
-                                                           want_depth ? -1.f : 0.f);
+        sgemm_bias_act_kernel<kActNone><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K,
+                                                              want_depth ? -1.f : 0.f);
         *is_depth = want_depth ? 1 : 0;
       }
       c->launches++;
@@ -742,7 +764,7 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
   if (!x_dev || !y_dev) return fail(PAYNE_E_INVALID, "null argument");
   if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
   if (ldy < c->D_out) return fail(PAYNE_E_INVALID, "ldy < D_out");
-  if (c->lay.precision != PAYNE_PREC_SIMT_FP32 && ((ldy & 3) || ((uintptr_t)y_dev & 15)))
+  if (!c->legacy && c->lay.precision != PAYNE_PREC_SIMT_FP32 && ((ldy & 3) || ((uintptr_t)y_dev & 15)))
     return fail(PAYNE_E_INVALID, "y_dev must be 16-byte aligned with ldy a multiple of 4 (TMA store)");
   if (B <= 0) return PAYNE_OK;
   CU_TRY(cudaSetDevice(c->device));

@@ -71,9 +71,21 @@ class Engine:
             W = [_f32(w) for w in spec.weights]
             b = [_f32(v) for v in spec.biases]
             keep += W + b
-            sp.D_in, sp.H1 = W[0].shape[1], W[0].shape[0]
-            sp.H2, sp.H3, sp.D_out = W[3].shape[0], W[4].shape[0], W[5].shape[0]
-            for k in range(6):
+            nl = len(W)
+            nntype = getattr(spec, 'nntype', 'LinNet')
+            if (nl, nntype) not in [(6, 'LinNet'), (4, 'SMLP'), (3, 'YST1')]:
+                raise ValueError('unsupported emulator: %d layers of type %s' % (nl, nntype))
+            sp.D_in, sp.H1, sp.D_out = W[0].shape[1], W[0].shape[0], W[-1].shape[0]
+            if nl == 6:          # NNmodels.py:147-152
+                sp.H2, sp.H3 = W[3].shape[0], W[4].shape[0]
+            elif nl == 4:        # NNmodels.py:99-107
+                sp.H2, sp.H3 = W[1].shape[0], W[2].shape[0]
+            else:                # ystpred.py:25-30
+                sp.H2, sp.H3 = W[1].shape[0], 0
+            sp.n_layers = nl
+            sp.activation = 0 if nntype == 'LinNet' else 1
+            sp.label_fp32_cast = 0 if nntype == 'YST1' else 1      # ystpred.py:47-50 stays in float64
+            for k in range(nl):
                 sp.W[k], sp.b[k] = _pf(W[k]), _pf(b[k])
             xmin, xmax, wave = _f64(spec.xmin), _f64(spec.xmax), _f64(spec.wavelength)
             keep += [xmin, xmax, wave]

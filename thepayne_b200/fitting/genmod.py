@@ -13,8 +13,14 @@ class GenMod(object):
         self.precision = kwargs.get('precision', 'parity')
 
     def _initspecnn(self, nnpath=None, **kwargs):          # genmod.py:15-32
-        NNtype = kwargs.get('NNtype', 'LinNet')
-        self.PP = PayneSpecPredict(nnpath=nnpath, NNtype=NNtype, precision=self.precision)
+        # the reference's own default here is 'YST1', but fitstar always passes NNtype and defaults
+        # it to 'LinNet' (fitstar.py:81); an in-memory network brings its own type
+        NNtype = kwargs.get('NNtype', getattr(nnpath, 'nntype', 'LinNet'))
+        if NNtype == 'YST1':                                # genmod.py:20-21
+            from ..predict.ystpred import PayneSpecPredict as YstPredict
+            self.PP = YstPredict(nnpath=nnpath, NNtype=NNtype, precision=self.precision)
+        else:
+            self.PP = PayneSpecPredict(nnpath=nnpath, NNtype=NNtype, precision=self.precision)
 
     def _initphotnn(self, filterarray, nnpath=None):       # genmod.py:35-43
         self.filterarray = None if filterarray is None else list(filterarray)

@@ -17,12 +17,12 @@ _FULL = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R']
 _FWHM = 2.355   # the kernel applies genmod.py:83's factor itself
 
 
-def _as_specnet(nnpath):
+def _as_specnet(nnpath, NNtype='LinNet'):
     if isinstance(nnpath, SpecNet):
         return nnpath
     if nnpath is None:
         raise IOError('no spectrum ANN given (the reference default data/ANN/NN.h5 is not shipped)')
-    return annio.load_specnet(nnpath)
+    return annio.load_specnet(nnpath, NNtype=NNtype)
 
 
 class ANN(object):
@@ -32,9 +32,11 @@ class ANN(object):
         self.verbose = kwargs.get('verbose', False)
         self.nnpath = nnpath
         self.NNtype = kwargs.get('NNtype', 'LinNet')
-        if self.NNtype != 'LinNet':
-            raise NotImplementedError('only the sigmoid LinNet is accelerated (NNtype=%r)' % self.NNtype)
-        self.model = _as_specnet(nnpath)
+        if self.NNtype not in ('LinNet', 'SMLP', 'YST1'):
+            raise NotImplementedError('NNtype=%r is not accelerated (LinNet, SMLP and YST1 are)' % self.NNtype)
+        self.model = _as_specnet(nnpath, self.NNtype)
+        if self.model.nntype != self.NNtype:
+            raise ValueError('NNtype=%r but the network container holds a %s' % (self.NNtype, self.model.nntype))
         self.inlabels = list(self.model.inlabels)
         self.xmin, self.xmax = self.model.xmin, self.model.xmax
         self.wavelength = self.model.wavelength

@@ -34,6 +34,9 @@ class SpecNet:
     resolution: float        # sigma-R of the emulator grid
     inlabels: list = field(default_factory=lambda: ['teff', 'logg', 'feh', 'afe'])
     encode_offset: float = 0.5   # LinNet subtracts 0.5 (NNmodels.py:166)
+    # 'LinNet' (6 x Linear, sigmoid; NNmodels.py:140-162), 'SMLP' (4 x Linear, LeakyReLU, torch fp32;
+    # NNmodels.py:92-115) or 'YST1' (3 layers, leaky ReLU, numpy fp64; predict/ystpred.py:18-58)
+    nntype: str = 'LinNet'
 
     @property
     def D_in(self):
@@ -41,7 +44,15 @@ class SpecNet:
 
     @property
     def D_out(self):
-        return int(self.weights[5].shape[0])
+        return int(self.weights[-1].shape[0])
+
+    @property
+    def n_layers(self):
+        return len(self.weights)
+
+    @property
+    def activation(self):
+        return 'sigmoid' if self.nntype == 'LinNet' else 'leaky'
 
     def digest(self) -> str:
         h = hashlib.sha256()
@@ -86,18 +97,21 @@ def ann_wavegrid(w0: float, w1: float, r_fwhm: float):
 
 
 def make_specnet(D_in, H, wave, resolution, seed=0, out_scale=0.3, out_bias=1.0,
-                 H2=None, H3=None):
+                 H2=None, H3=None, nntype='LinNet'):
     """Random-init LinNet: default torch init, then lin6.weight*=0.3 and
-    lin6.bias=1 so the emulated flux looks like a normalised spectrum (1 +/- 0.07)."""
+    lin6.bias=1 so the emulated flux looks like a normalised spectrum (1 +/- 0.07).
+    ``nntype`` 'SMLP' / 'YST1' build the legacy leaky-ReLU stacks (4 / 3 layers) the same way."""
     H2 = H if H2 is None else H2
     H3 = H if H3 is None else H3
     D_out = len(wave)
     torch.manual_seed(seed)
-    dims = [(D_in, H), (H, H), (H, H2), (H2, H2), (H2, H3), (H3, D_out)]
+    dims = {'LinNet': [(D_in, H), (H, H), (H, H2), (H2, H2), (H2, H3), (H3, D_out)],
+            'SMLP': [(D_in, H), (H, H2), (H2, H3), (H3, D_out)],          # NNmodels.py:99-107
+            'YST1': [(D_in, H), (H, H2), (H2, D_out)]}[nntype]            # ystpred.py:25-30
     lins = [torch.nn.Linear(i, o) for i, o in dims]
     with torch.no_grad():
-        lins[5].weight *= out_scale
-        lins[5].bias.fill_(out_bias)
+        lins[-1].weight *= out_scale
+        lins[-1].bias.fill_(out_bias)
     xmin = np.array([3500.0, 0.0, -2.5, -0.2, 0.5][:D_in])
     xmax = np.array([8000.0, 5.5, 0.5, 0.6, 3.0][:D_in])
     labels = ['teff', 'logg', 'feh', 'afe', 'vmic'][:D_in]
@@ -105,7 +119,7 @@ def make_specnet(D_in, H, wave, resolution, seed=0, out_scale=0.3, out_bias=1.0,
         weights=[l.weight.detach().numpy().copy() for l in lins],
         biases=[l.bias.detach().numpy().copy() for l in lins],
         xmin=xmin, xmax=xmax, wavelength=np.asarray(wave, dtype=np.float64),
-        resolution=float(resolution), inlabels=labels)
+        resolution=float(resolution), inlabels=labels, nntype=nntype)
 
 
 # A few rows of the reference's high-Av table (highred.py:29-169) are needed by the
@@ -193,12 +207,12 @@ PROCYON_BANDS = ['Bessell_B', 'Bessell_V', 'Bessell_R', 'Bessell_I',
 def build_config(name, *, model_fn, ann_range=(5130.0, 5340.0), r_fwhm=50000.0,
                  obs_range=(5150.0, 5320.0), n_obs=7000, H=256, vmic=False,
                  npoly=0, bands=None, photscale=True, photH=128, vrot_max=5.0,
-                 snr=50.0, seed_net=0, seed_noise=3, obs_wave=None):
+                 snr=50.0, seed_net=0, seed_noise=3, obs_wave=None, nntype='LinNet'):
     """Assemble a SynthConfig. ``model_fn(cfg, theta[1,ndim]) -> (flux[1,n_obs], mags)``
     supplies the noiseless model at the truth (the oracle, passed in by the caller so
     that this module has no dependency on ``oracle/``)."""
     wave, rsig = ann_wavegrid(ann_range[0], ann_range[1], r_fwhm)
-    spec = make_specnet(5 if vmic else 4, H, wave, rsig, seed=seed_net)
+    spec = make_specnet(5 if vmic else 4, H, wave, rsig, seed=seed_net, nntype=nntype)
     if obs_wave is None:
         obs_wave = np.linspace(obs_range[0], obs_range[1], n_obs)
     fit = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot']

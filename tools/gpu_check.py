@@ -55,7 +55,9 @@ def main():
             yr = L.net(x)
             print('   ann_eval max rel %.2e' % np.max(np.abs(y - yr) / np.abs(yr)), flush=True)
             lh = eng.lnlike_batch(g['theta'])
-            print('   host entry == device entry:', np.array_equal(np.nan_to_num(lh, nan=1.0), np.nan_to_num(lnl, nan=1.0)))
+            ld = eng.lnlike_batch(th).cpu().numpy()          # same lnL-only path (model_batch's lnL goes through the stored spectrum)
+            print('   host entry == device entry:', np.array_equal(np.nan_to_num(lh, nan=1.0), np.nan_to_num(ld, nan=1.0)),
+                  ' max|lnL-only - via spectrum| %.2e' % np.nanmax(np.abs(ld - lnl)))
         if name == 'c2':
             B = 4096
             thb = torch.from_numpy(cfg.draw(B)).cuda()
