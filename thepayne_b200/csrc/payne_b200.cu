@@ -509,6 +509,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
     CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
+    CU_TRY(cudaMemset(c->fast.points, 0, (size_t)rows * sizeof(payne::FastPoint)));   // struct padding is copied too
     int rc = payne::tc_alloc_acts(&c->actA, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
     rc = payne::tc_alloc_acts(&c->actB, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
   }
