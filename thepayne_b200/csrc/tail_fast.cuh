@@ -16,6 +16,13 @@
 #include "tail.cuh"
 #include "tail_general.cuh"
 
+// Resident CTAs per SM the register budget is sized for (transforms up to 16384 samples).  Measured at
+// C2: 3 (80 registers, a few spills) 0.76 ms; 2 (128 registers, no spills) 0.84 ms -- the convolution
+// core alone is 3 % faster with 2, but the latency-bound regrid / final phases lose a third of their warps.
+#ifndef PAYNE_TAIL_MINB
+#define PAYNE_TAIL_MINB 3
+#endif
+
 namespace payne {
 
 struct FastGrid {
@@ -218,7 +225,7 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
 // LOG2N1 <= 15: the whole transform sits in shared memory (3 CTAs/SM up to 2^14).
 // LOG2N1 == 16: split transform, half in shared memory (128 KB), half in the scratch line.
 template <int LOG2N1>
-__global__ void __launch_bounds__(kNT, LOG2N1 <= 14 ? 3 : 1)
+__global__ void __launch_bounds__(kNT, LOG2N1 <= 14 ? PAYNE_TAIL_MINB : 1)
 tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);
