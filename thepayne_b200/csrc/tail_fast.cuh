@@ -181,26 +181,37 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
   const double q0 = FS.q0, scale = FS.scale;
   double acc = 0.0;
   if (P.n_poly == 0 && P.model_out == nullptr) {
-    int j = tid;
-    double q = 0.0, is = 0.0, ot = 0.0;
-    if (j < P.n_obs) { q = __ldcg(F.obs_q + j); is = __ldcg(P.obs_inv_s + j); ot = __ldcg(F.obs_otm1 + j); }
-#pragma unroll 2
-    for (; j < P.n_obs; j += kNT) {
-      const int jn = j + kNT;
-      double qn = 0.0, isn = 0.0, otn = 0.0;       // next pixel's constants, requested early
-      if (jn < P.n_obs) { qn = __ldcg(F.obs_q + jn); isn = __ldcg(P.obs_inv_s + jn); otn = __ldcg(F.obs_otm1 + jn); }
-      const double pp = (q - q0) * scale;
-      double r;
-      if (!(pp >= 0.0 && pp <= pmax)) r = nan;                 // smoothing.py:289 left/right = nan
-      else {
-        const int k = min((int)pp, N2 - 2);
-        const float dl = (float)(pp - (double)k);
-        const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
-        const float d = fmaf(interp_w(dl, hdu), g1 - g0, g0);
-        r = fma((double)d, is, -ot);
+    // four pixels per trip: the twelve per-pixel constants are requested together, then the eight
+    // shared-memory samples, then the arithmetic (the phase is latency-bound at 24 warps per SM)
+    constexpr int U = 4;
+#pragma unroll 1
+    for (int j0 = tid; j0 < P.n_obs; j0 += U * kNT) {
+      double q[U], is[U], ot[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * kNT;
+        const bool in = j < P.n_obs;
+        q[u] = in ? __ldcg(F.obs_q + j) : -1.0;          // -1 -> outside the grid -> contributes through `in` only
+        is[u] = in ? __ldcg(P.obs_inv_s + j) : 0.0;
+        ot[u] = in ? __ldcg(F.obs_otm1 + j) : 0.0;
       }
-      acc = fma(r, r, acc);
-      q = qn; is = isn; ot = otn;
+      float g0[U], g1[U], dl[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double pp = (q[u] - q0) * scale;
+        ok[u] = (pp >= 0.0 && pp <= pmax);               // smoothing.py:289 left/right = nan
+        const int k = ok[u] ? min((int)pp, N2 - 2) : 0;
+        dl[u] = (float)(pp - (double)k);
+        g0[u] = zv.ld(k); g1[u] = zv.ld(k + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float d = fmaf(interp_w(dl[u], hdu), g1[u] - g0[u], g0[u]);
+        double r = fma((double)d, is[u], -ot[u]);
+        if (!ok[u]) r = nan;
+        if (j0 + u * kNT < P.n_obs) acc = fma(r, r, acc);
+      }
     }
   } else {
     for (int j = tid; j < P.n_obs; j += kNT) {
