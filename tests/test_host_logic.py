@@ -91,3 +91,22 @@ def test_polycalc_is_chebval_on_normalised_grid():
     w = np.linspace(5150, 5320, 50)
     c = np.array([1.0, 0.02, -0.01])
     assert np.array_equal(polycalc(c, w), O.polycalc(c, w))
+
+
+def test_legacy_network_containers_round_trip(tmp_path):
+    """SMLP (model/features.*) and YST1 (w_array_* / x_min / wavelength) layouts of the reference's
+    files (NNmodels.py:51-63, ystpred.py:25-37) through both containers; the type is inferred from the
+    dataset names when not given."""
+    from thepayne_b200 import annio, synth
+    w = synth.ann_wavegrid(5150.0, 5160.0, 1e5)[0][:300]
+    for nntype, H, nl in [('LinNet', 32, 6), ('SMLP', 24, 4), ('YST1', 16, 3)]:
+        net = synth.make_specnet(4, H, w, 1e5, seed=1, nntype=nntype)
+        assert net.n_layers == nl and net.activation == ('sigmoid' if nl == 6 else 'leaky')
+        for ext in ['npz', 'h5']:
+            p = str(tmp_path / ('%s.%s' % (nntype, ext)))
+            annio.save_specnet(p, net)
+            back = annio.load_specnet(p)
+            assert back.nntype == nntype and back.n_layers == nl and back.resolution == net.resolution
+            assert all(np.array_equal(a, b) for a, b in zip(net.weights + net.biases, back.weights + back.biases))
+            assert np.array_equal(back.wavelength, net.wavelength) and np.array_equal(back.xmax, net.xmax)
+            assert annio.load_specnet(p, NNtype=nntype).D_out == net.D_out
