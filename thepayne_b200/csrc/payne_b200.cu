@@ -514,6 +514,9 @@ int ensure_workspace(PayneCtx* c, long long B) {
     rc = payne::tc_alloc_acts(&c->actB, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
   }
   CU_TRY(cudaMalloc((void**)&c->chi2_sed, (size_t)rows * sizeof(double)));
+  // the zero-fills above went to the NULL stream; callers may launch on non-blocking streams that do
+  // not order against it, so finish them here (allocation happens once per workspace size)
+  CU_TRY(cudaDeviceSynchronize());
   c->slab_alloc = need;
   return PAYNE_OK;
 }
