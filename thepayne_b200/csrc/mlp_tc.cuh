@@ -113,6 +113,8 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // ---- cta_group::2 (two SMs on one tile) ----
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even CTA
@@ -216,16 +218,30 @@ __host__ __device__ constexpr uint32_t umma_idesc(int N, uint32_t fmt) {
 
 // fixed-point slices of the exact-accumulation split -----------------------------------------
 // activations (0 <= h < ~1): p1 = rint(h 2^8) 2^-8, p2 = rint(r1 2^16) 2^-16, p3 = rint(r2 2^24) 2^-24
+// Rounding to a multiple of 2^-s is done by adding and subtracting 1.5 * 2^(23-s): in that binade one
+// ulp is 2^-s, so the fp32 add itself rounds (to nearest, ties to even) exactly like rintf(h 2^s) 2^-s,
+// without the three conversions per element that kept the epilogue on the slow XU pipe.
+__device__ __forceinline__ float round_to_pow2_grid(float x, float magic) {
+  return __fsub_rn(__fadd_rn(x, magic), magic);
+}
 __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bfloat16& p2, __nv_bfloat16& p3) {
-  const float a1 = rintf(h * 256.f) * (1.f / 256.f);
+  const float a1 = round_to_pow2_grid(h, 49152.f);          // 1.5 * 2^15 : grid 2^-8
   const float r1 = h - a1;
-  const float a2 = rintf(r1 * 65536.f) * (1.f / 65536.f);
+  const float a2 = round_to_pow2_grid(r1, 192.f);           // 1.5 * 2^7  : grid 2^-16
   const float r2 = r1 - a2;
-  const float a3 = rintf(r2 * 16777216.f) * (1.f / 16777216.f);
+  const float a3 = round_to_pow2_grid(r2, 0.75f);           // 1.5 * 2^-1 : grid 2^-24
   p1 = __float2bfloat16_rn(a1); p2 = __float2bfloat16_rn(a2); p3 = __float2bfloat16_rn(a3);
 }
 
 constexpr int kTcThreads = 256;
+// Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get a
+// second group of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and
+// took more than half of the kernel; two groups split the column chunks.
+template <int MODE, int EPI>
+struct TcThreads {
+  static constexpr int kEpiWarps = (EPI == 1 && MODE == kModeX3) ? 8 : 4;
+  static constexpr int value = 128 + 32 * kEpiWarps;
+};
 constexpr int kBM = 128;
 constexpr int kRowBytes = 128;   // one swizzle row: 32 tf32 or 64 bf16 along K
 
@@ -313,7 +329,7 @@ struct TcGemmArgs {
 // each loads half of the weight rows and TMA-multicasts them to both, so the weight operand
 // crosses L2->SMEM once per pair (the GEMM is bound by that traffic: K is only 256..512).
 template <int BN, int MODE, int EPI, int MC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(TcThreads<MODE, EPI>::value, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
   using Cfg = TcCfg<BN, MODE>;
   constexpr int NS = Cfg::kStages, NP = Cfg::kPlanes;
@@ -345,7 +361,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], MC ? 2 : 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], TcThreads<MODE, EPI>::kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -437,13 +453,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
       if constexpr (EPI == 0 || kRegEpi) {
         // bias (+shift) and scale of this tile's columns -> shared memory, before the accumulator
         // is awaited so the loads are off the critical path
-        ptx::epi_bar_sync();                       // previous tile's readers are done
-        for (int cix = threadIdx.x - 128; cix < BN; cix += 128) {
+        constexpr int kEpiThreads = 32 * TcThreads<MODE, EPI>::kEpiWarps;
+        ptx::epi_bar_sync_n<kEpiThreads>();        // previous tile's readers are done
+        for (int cix = threadIdx.x - 128; cix < BN; cix += kEpiThreads) {
           const int gc = n0 + cix;
           sbias[cix] = (gc < G.N ? __ldg(G.bias + gc) : 0.f) + G.bias_shift;
           sscale[cix] = (MODE == kModeX3 && gc < G.N) ? __ldg(G.wscale + gc) : 1.f;
         }
-        ptx::epi_bar_sync();
+        ptx::epi_bar_sync_n<kEpiThreads>();
       }
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
@@ -466,8 +483,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
         // row's 64 bytes are contiguous, so the stores fill whole sectors without a transpose).
         const int grow = row_base + lane;
         const bool rowok = grow < G.M;
+        const int grp = (warp - 4) >> 2;           // two groups of four warps split the column chunks
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = grp; ch < BN / 32; ch += TcThreads<MODE, EPI>::kEpiWarps / 4) {
           const int col0 = n0 + ch * 32;
           if (col0 >= G.N) break;
           uint32_t v[32], c[32];
@@ -953,7 +971,7 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
     const int pair_tiles = ((num_m + 1) / 2) * num_n;
     int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TcThreads<MODE, EPI>::value); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -962,7 +980,7 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
   } else {
     const int tiles = num_m * num_n;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    tc_gemm_kernel<BN, MODE, EPI, MC><<<grid, kTcThreads, Cfg::kSmem, st>>>(T, G);
+    tc_gemm_kernel<BN, MODE, EPI, MC><<<grid, TcThreads<MODE, EPI>::value, Cfg::kSmem, st>>>(T, G);
   }
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
