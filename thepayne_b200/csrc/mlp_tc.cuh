@@ -193,6 +193,14 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -234,12 +242,12 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
 }
 
 constexpr int kTcThreads = 256;
-// Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get a
-// second group of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and
-// took more than half of the kernel; two groups split the column chunks.
+// Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get four
+// groups of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and took more
+// than half of the kernel; each group takes 16 of the tile's 64 columns.
 template <int MODE, int EPI>
 struct TcThreads {
-  static constexpr int kEpiWarps = (EPI == 1 && MODE == kModeX3) ? 8 : 4;
+  static constexpr int kEpiWarps = (EPI == 1 && MODE == kModeX3) ? 16 : 4;
   static constexpr int value = 128 + 32 * kEpiWarps;
 };
 constexpr int kBM = 128;
@@ -483,20 +491,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
         // row's 64 bytes are contiguous, so the stores fill whole sectors without a transpose).
         const int grow = row_base + lane;
         const bool rowok = grow < G.M;
-        const int grp = (warp - 4) >> 2;           // two groups of four warps split the column chunks
-#pragma unroll 1
-        for (int ch = grp; ch < BN / 32; ch += TcThreads<MODE, EPI>::kEpiWarps / 4) {
-          const int col0 = n0 + ch * 32;
-          if (col0 >= G.N) break;
-          uint32_t v[32], c[32];
-          ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
-          ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
+        constexpr int NG = TcThreads<MODE, EPI>::kEpiWarps / 4, CW = BN / NG;   // column groups, columns each
+        static_assert(CW == 16, "hidden-layer epilogue: 16 columns per warp group");
+        const int grp = (warp - 4) >> 2;
+        const int cbase = grp * CW, col0 = n0 + cbase;
+        if (col0 < G.N) {
+          uint32_t v[CW], c[CW];
+          ptx::tmem_ld16_nowait(t_main + (uint32_t)cbase, v);
+          ptx::tmem_ld16_nowait(t_main + (uint32_t)(BN + cbase), c);
           ptx::tmem_ld_wait();
           const long long o = (long long)grow * G.ldc + col0;
-          const float4* b4 = reinterpret_cast<const float4*>(sbias + ch * 32);
-          const float4* s4 = reinterpret_cast<const float4*>(sscale + ch * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + cbase);
+          const float4* s4 = reinterpret_cast<const float4*>(sscale + cbase);
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
+          for (int g8 = 0; g8 < CW / 8; ++g8) {
             __align__(16) __nv_bfloat16 q1[8], q2[8], q3[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
