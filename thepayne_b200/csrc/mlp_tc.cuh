@@ -241,6 +241,9 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
   p1 = __float2bfloat16_rn(a1); p2 = __float2bfloat16_rn(a2); p3 = __float2bfloat16_rn(a3);
 }
 
+#ifndef PAYNE_GEMM_2SM_DEFAULT
+#define PAYNE_GEMM_2SM_DEFAULT 0
+#endif
 constexpr int kTcThreads = 256;
 // Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get four
 // groups of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and took more
@@ -284,6 +287,35 @@ __device__ __forceinline__ void epi_store_block(const CUtensorMap* cmap, float* 
   ptx::fence_async_smem();
   __syncwarp();
   if (lane == 0) ptx::tma_store_2d(cmap, stage, gcol0, grow0);
+}
+
+// Staging-free variant for the pair-tile kernel (its three-stage ring leaves no shared memory for the
+// TMA-store blocks): thread = row, whose 32 columns are 128 contiguous bytes, written as eight 16-byte
+// stores -- every store fills half a sector of its own line, the eight together the whole line.
+__device__ __forceinline__ void epi_store_direct(float* out, long long ldc, int M, int N, const float* sb,
+                                                 const float* ss, const uint32_t (&v)[32], const uint32_t (&c)[32],
+                                                 int colbase, int gcol0, int grow) {
+  if (grow >= M) return;
+  const float4* b4 = reinterpret_cast<const float4*>(sb + colbase);
+  const float4* s4 = reinterpret_cast<const float4*>(ss + colbase);
+  float* dst = out + (long long)grow * ldc + gcol0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 bb = b4[k], sc = s4[k];
+    float4 o;
+    o.x = fmaf(__uint_as_float(v[4 * k + 0]) + __uint_as_float(c[4 * k + 0]), sc.x, bb.x);
+    o.y = fmaf(__uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1]), sc.y, bb.y);
+    o.z = fmaf(__uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]), sc.z, bb.z);
+    o.w = fmaf(__uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]), sc.w, bb.w);
+    const int gc = gcol0 + 4 * k;
+    if (gc + 4 <= N) {
+      *reinterpret_cast<float4*>(dst + 4 * k) = o;
+    } else {
+      if (gc + 0 < N) dst[4 * k + 0] = o.x;
+      if (gc + 1 < N) dst[4 * k + 1] = o.y;
+      if (gc + 2 < N) dst[4 * k + 2] = o.z;
+    }
+  }
 }
 
 template <int BN, int MODE>
@@ -609,23 +641,39 @@ __host__ __device__ constexpr uint32_t umma_idesc_m256(int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int EPI>
+// BN = 256: one 512-column accumulator pair, 2-deep ring (epilogue exposed).  BN = 128: the pair tile is
+// 256 x 128, each CTA stages its 128 activation rows and 64 of the weight rows (72 KB per k-block instead
+// of 96 KB for the single-CTA 128 x 128 tile), which buys a 3-deep ring, and two accumulator pairs fit
+// the 512 TMEM columns so the epilogue overlaps the next tile's MMAs.
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int BNH = BN / 2, NP = 3;
+  static constexpr int NS = BN == 128 ? 3 : 2;
+  static constexpr int NACC = BN == 128 ? 2 : 1;
+  static constexpr int kABytes = kBM * kRowBytes, kBBytes = BNH * kRowBytes;
+  static constexpr int kStageBytes = NP * (kABytes + kBBytes);          // per CTA
+  static constexpr int kStagingBytes = BN == 128 ? 0 : 4 * 4096;       // TMA-store staging (BN = 128 stores directly)
+  static constexpr int kSmem = NS * kStageBytes + kStagingBytes + 1024 + 256 + 2 * BN * 4;
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+template <int EPI, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
-  constexpr int BN = 256, BNH = 128, NP = 3, NS = 2;
-  constexpr int kABytes = kBM * kRowBytes, kBBytes = BNH * kRowBytes;
-  constexpr int kStageBytes = NP * (kABytes + kBBytes);          // per CTA
+  using C2 = Tc2Cfg<BN>;
+  constexpr int BNH = C2::BNH, NP = C2::NP, NS = C2::NS, NACC = C2::NACC;
+  constexpr int kABytes = C2::kABytes, kBBytes = C2::kBBytes, kStageBytes = C2::kStageBytes;
   constexpr int kBK = 64;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* stages = base;
   float* patch = (float*)(base + NS * kStageBytes);
-  uint64_t* bars = (uint64_t*)((unsigned char*)patch + 4 * 32 * 33 * 4);
+  uint64_t* bars = (uint64_t*)((unsigned char*)patch + C2::kStagingBytes);
   uint64_t* full = bars;             // [NS]  used in the leader: 2 arrivals + bytes of both CTAs
   uint64_t* empty = bars + NS;       // [NS]  per CTA: multicast commit of the leader
-  uint64_t* tfull = bars + 2 * NS;   // per CTA: multicast commit of the leader
-  uint64_t* tempty = tfull + 1;      // leader: 8 epilogue warps (both CTAs)
-  uint32_t* tmem_ptr = (uint32_t*)(tempty + 1);
+  uint64_t* tfull = bars + 2 * NS;   // [NACC] per CTA: multicast commit of the leader
+  uint64_t* tempty = tfull + NACC;   // [NACC] leader: 8 epilogue warps (both CTAs)
+  uint32_t* tmem_ptr = (uint32_t*)(tempty + NACC);
   float* sbias = (float*)(bars + 32);
   float* sscale = sbias + BN;
 
@@ -642,8 +690,7 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 2); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(tfull, 1);
-    ptx::mbar_init(tempty, 8);
+    for (int a = 0; a < NACC; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 8); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr, 512);
@@ -679,11 +726,11 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_m256(BN, 1u);
       int s = 0; uint32_t ph = 0;
-      uint32_t aph = 0;
+      int acc = 0; uint32_t aph = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        ptx::mbar_wait_cluster(tempty, aph ^ 1);
+        ptx::mbar_wait_cluster(&tempty[acc], aph ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN), d_corr = d_main + BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait_cluster(&full[s], ph);
           ptx::tc_fence_after();
@@ -706,17 +753,17 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
             ptx::mma_bf16_2sm(d_corr, da[1] + ko, db[0] + ko, idesc, 1);
           }
           ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)3);
-          if (kb == num_kb - 1) ptx::mma_commit_2sm_mc(tfull, (uint16_t)3);
+          if (kb == num_kb - 1) ptx::mma_commit_2sm_mc(&tfull[acc], (uint16_t)3);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
-        aph ^= 1;
+        if (++acc == NACC) { acc = 0; aph ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;
-    float* pt = patch + q * 1024;
-    uint32_t aph = 0;
+    float* pt = patch + q * (C2::kStagingBytes / 16);
+    int acc = 0; uint32_t aph = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = (tile / num_n) * 256 + (int)crank * 128, n0 = (tile % num_n) * BN;
       ptx::epi_bar_sync();
@@ -726,10 +773,10 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
         sscale[cix] = gc < G.N ? __ldg(G.wscale + gc) : 1.f;
       }
       ptx::epi_bar_sync();
-      ptx::mbar_wait_cluster(tfull, aph);
+      ptx::mbar_wait_cluster(&tfull[acc], aph);
       ptx::tc_fence_after();
       const int row_base = m0 + q * 32;
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col0 = n0 + ch * 32;
@@ -738,12 +785,15 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
         ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
         ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
         ptx::tmem_ld_wait();
-        epi_store_block<true>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
+        if constexpr (BN == 128)
+          epi_store_direct((float*)G.out0, G.ldc, G.M, G.N, sbias, sscale, v, c, ch * 32, col0, row_base + lane);
+        else
+          epi_store_block<true>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_leader(tempty);
-      aph ^= 1;
+      if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
+      if (++acc == NACC) { acc = 0; aph ^= 1; }
     }
     if (lane == 0) ptx::tma_store_wait_all();
   }
@@ -843,13 +893,13 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // 2-D row-major [rows, K] (pitch ld elements) -> boxes of {128 bytes of K, box_rows}, 128B swizzle
 // fp32 output [rows, cols] with pitch ld floats -> 32 x 32 boxes, 128B swizzle (TMA store)
-inline int make_tmap_out(CUtensorMap* m, const void* ptr, long long rows, int cols, long long ld) {
+inline int make_tmap_out(CUtensorMap* m, const void* ptr, long long rows, int cols, long long ld, int box_rows = 32) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return PAYNE_E_CUDA;
   if ((ld & 3) || ((uintptr_t)ptr & 15)) return PAYNE_E_INVALID;   // TMA: 16-byte base and pitch
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -993,38 +1043,42 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
-// PAYNE_GEMM_2SM=0 falls back to the single-CTA tiles for lin6.
-inline bool tc_2sm_enabled() {
+// PAYNE_GEMM_2SM selects the cta_group::2 pair-tile kernel for lin6: 1 = 256 x 128 pair tiles (3-deep ring,
+// double-buffered accumulators), 2 = 256 x 256 pair tiles (single accumulator pair, epilogue exposed),
+// 0 = single-CTA 128 x 128 tiles.
+inline int tc_2sm_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PAYNE_GEMM_2SM"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v != 0;
+  if (v < 0) { const char* e = getenv("PAYNE_GEMM_2SM"); v = e ? atoi(e) : PAYNE_GEMM_2SM_DEFAULT; if (v < 0 || v > 2) v = 0; }
+  return v;
 }
 
+template <int BN>
 inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, long long ldc,
-                         float bias_shift, int M, int sm_count, cudaStream_t st) {
-  constexpr int kSmem = 2 * 3 * (kBM * kRowBytes + 128 * kRowBytes) + 4 * 32 * 33 * 4 + 1024 + 256 + 2 * 256 * 4;
+                         float bias_shift, int M, int sm_count, cudaStream_t st, long long map_rows) {
+  using C2 = Tc2Cfg<BN>;
+  const long long mrows = map_rows >= M ? map_rows : M;
   TcMaps T;
   for (int p = 0; p < 3; ++p) {
-    if (make_tmap(&T.a[p], A.plane[p], M, K, A.ld, kBM, 2)) return PAYNE_E_CUDA;
-    if (make_tmap(&T.b[p], W.xplane[p], W.N, K, W.Kp, 128, 2)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.a[p], A.plane[p], mrows, K, A.ld, kBM, 2)) return PAYNE_E_CUDA;
+    if (make_tmap(&T.b[p], W.xplane[p], W.N, K, W.Kp, C2::BNH, 2)) return PAYNE_E_CUDA;
   }
-  if (int rc = make_tmap_out(&T.c, out0, M, W.N, ldc)) return rc;
+  if (int rc = make_tmap_out(&T.c, out0, mrows, W.N, ldc)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm2_kernel<0, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem) != cudaSuccess)
       return PAYNE_E_CUDA;
     attr_set = true;
   }
   TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K};
-  const int pair_tiles = ((M + 255) / 256) * ((W.N + 255) / 256);
+  const int pair_tiles = ((M + 255) / 256) * ((W.N + BN - 1) / BN);
   const int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = C2::kSmem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<0>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
+  if (cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<0, BN>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
@@ -1032,8 +1086,10 @@ template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                      void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
                      TcMapCache* cache = nullptr, long long map_rows = 0) {
-  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_enabled())
-    return tc_launch_2sm(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st);
+  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 1)
+    return tc_launch_2sm<128>(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st, map_rows);
+  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 2)
+    return tc_launch_2sm<256>(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st, map_rows);
   // multicast pays when many row tiles share each weight tile (the wide last layer)
   if (EPI == 0 && BN >= 128 && M > kBM && tc_multicast_enabled())
     return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
