@@ -241,6 +241,10 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
   p1 = __float2bfloat16_rn(a1); p2 = __float2bfloat16_rn(a2); p3 = __float2bfloat16_rn(a3);
 }
 
+// output-layer tile width; 64 (3-deep ring) was measured slower: MLP 0.274 vs 0.195 ms (A tile re-read twice as often)
+#ifndef PAYNE_LIN6_BN
+#define PAYNE_LIN6_BN 128
+#endif
 #ifndef PAYNE_GEMM_2SM_DEFAULT
 #define PAYNE_GEMM_2SM_DEFAULT 0
 #endif
@@ -1124,7 +1128,7 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
     TcActs* t = cur; cur = nxt; nxt = t;
   }
   if (rc) return rc;
-  rc = tc_launch<128, MODE, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, nullptr, ldo, bias_shift, nb,
+  rc = tc_launch<PAYNE_LIN6_BN, MODE, 0>(*cur, dims_in[5], tcw[5], bias[5], out, nullptr, nullptr, ldo, bias_shift, nb,
                                sm_count, st, caches ? caches + 5 : nullptr, out_rows >= cur->rows ? cur->rows : 0);
   ++*launches;
   return rc;
