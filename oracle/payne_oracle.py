@@ -74,14 +74,28 @@ class LegacyNet:
     ``YST1`` (``predict/ystpred.py:47-58``): numpy all the way -- float64 labels, the stored weight
     arrays as they are, ``z*(z>0) + 0.01*z*(z<0)``, three ``einsum`` layers."""
 
-    def __init__(self, spec):
+    def __init__(self, spec, ideal=False):
+        """``ideal=True``: the SMLP evaluated in float64 (yardstick for the reference's own fp32 round-off;
+        YST1 already is float64 in the reference)."""
         self.spec = spec
+        self.ideal = ideal
 
     def __call__(self, x):
         sp = self.spec
         x = np.asarray(x, dtype=np.float64)
         if x.ndim == 1:
             x = x[None, :]
+        if sp.nntype == 'SMLP' and self.ideal:
+            x32 = torch.from_numpy(x).type(torch.FloatTensor)
+            enc = (x32.numpy() - sp.xmin) / (sp.xmax - sp.xmin) - 0.5
+            h = torch.from_numpy(enc).type(torch.FloatTensor).double()
+            with torch.no_grad():
+                for k in range(3):
+                    h = torch.nn.functional.leaky_relu(torch.nn.functional.linear(
+                        h, torch.from_numpy(sp.weights[k]).double(), torch.from_numpy(sp.biases[k]).double()))
+                y = torch.nn.functional.linear(h, torch.from_numpy(sp.weights[3]).double(),
+                                               torch.from_numpy(sp.biases[3]).double())
+            return y.numpy()
         if sp.nntype == 'SMLP':
             x32 = torch.from_numpy(x).type(torch.FloatTensor)
             enc = (x32.numpy() - sp.xmin) / (sp.xmax - sp.xmin) - 0.5
@@ -104,7 +118,7 @@ class LegacyNet:
 
 
 def make_net(spec, ideal=False):
-    return TorchLinNet(spec, ideal=ideal) if spec.nntype == 'LinNet' else LegacyNet(spec)
+    return TorchLinNet(spec, ideal=ideal) if spec.nntype == 'LinNet' else LegacyNet(spec, ideal=ideal)
 
 
 # --------------------------------------------------------------------------- smoothing

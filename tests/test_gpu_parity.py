@@ -289,3 +289,15 @@ def test_legacy_nets_through_the_mirrors(tmp_path, name, nntype):
     y = like.GM.PP.anns.eval(list(g['theta'][0][:4]))
     yo = O.make_net(cfg.spec)(g['theta'][0][:4])[0]
     assert np.max(np.abs(y - yo)) < 2e-6
+
+
+def test_differential_fuzz_against_the_oracle():
+    """Random small configurations (emulator range / width / type, observed grids sticking out of the
+    coverage, continuum orders, photometry, wide parameter boxes) through tools/gpu_fuzz.py: NaN patterns
+    identical, flux <= 1e-5, lnL within max(1e-3, 1e-8 |lnL|) -- or, where the reference's own fp32
+    round-off exceeds that (far-off points, |lnL| ~ 1e5), at least as close to the exact-arithmetic
+    (float64 emulator) value as the reference is."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import gpu_fuzz
+    assert gpu_fuzz.run(seed=1, ncfg=14, verbose=False) == 0
