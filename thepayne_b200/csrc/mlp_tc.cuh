@@ -371,7 +371,7 @@ struct TcGemmArgs {
 
 // MC = 1: the CTAs of a 2-CTA cluster work on the SAME weight tile for two different row tiles;
 // each loads half of the weight rows and TMA-multicasts them to both, so the weight operand
-// crosses L2->SMEM once per pair (the GEMM is bound by that traffic: K is only 256..512).
+// crosses L2->SMEM once per pair (measured: -25 % L2 reads, no change in time; see tc_multicast_enabled).
 template <int BN, int MODE, int EPI, int MC>
 __global__ void __launch_bounds__(TcThreads<MODE, EPI>::value, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
@@ -635,12 +635,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
 }
 
 // ------------------------------------------------------------------------------------------------
-// lin6 on CTA PAIRS (cta_group::2): a 2-CTA cluster owns a 256 x 256 output tile; CTA r holds rows
-// [128 r, 128 r + 128) of the activations and weight rows [128 r, +128) of the tile, the leader
+// lin6 on CTA PAIRS (cta_group::2): a 2-CTA cluster owns a 256 x BN output tile; CTA r holds rows
+// [128 r, 128 r + 128) of the activations and weight rows [BN/2 r, +BN/2) of the tile, the leader
 // (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) and each SM accumulates its 128 rows in its own
-// TMEM.  Inbound operand traffic per SM halves relative to the 128 x 128 single-CTA tiles
-// (96 KB per 3072 MMA-cycles instead of per 1536), which is what bounds this K = 256 GEMM.
-// X3 only: the two accumulators take all 512 TMEM columns, so the epilogue is not overlapped.
+// TMEM.  Inbound operand traffic per SM drops relative to the 128 x 128 single-CTA tiles.  X3 only.
+// Measured on B200: bit-exact, but 50 % tensor-pipe utilisation against 74 % for the single-CTA kernel
+// (profiles/r01_gemm_l6_pairtile.txt) -- opt-in until that is understood.
 __host__ __device__ constexpr uint32_t umma_idesc_m256(int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
