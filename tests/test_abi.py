@@ -30,7 +30,9 @@ def test_header_symbols_are_exported(lib):
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.payne_abi_version() == 2
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'payne_b200.h')).read()
+    assert lib.payne_abi_version() == int(re.search(r'#define\s+PAYNE_ABI_VERSION\s+(\d+)', hdr).group(1))
 
 
 def test_struct_layout_matches_header(lib, tmp_path):
