@@ -330,8 +330,10 @@ struct TcCfg {
   static constexpr int kUmmaK = 32 / kElemBytes;                  // K per MMA
   static constexpr int kABytes = kBM * kRowBytes, kBBytes = BN * kRowBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kPatchBytes = 4 * 32 * 33 * 4;
-  static constexpr int kBudget = 220 * 1024 - kPatchBytes - 1024;
+  // epilogue staging (TMA-store blocks / transpose patches); the 64-wide parity tiles are the hidden
+  // layers, whose epilogue stays in registers, so their ring gets the space: 3 stages instead of 2
+  static constexpr int kPatchBytes = (MODE == kModeX3 && BN == 64) ? 0 : 4 * 32 * 33 * 4;
+  static constexpr int kBudget = 232448 - kPatchBytes - 1024 - 256 - 2 * BN * 4;
   static constexpr int kStages = (kBudget / kStageBytes) > 6 ? 6 : (kBudget / kStageBytes);
   static constexpr int kSmem = kStages * kStageBytes + kPatchBytes + 1024 /*align*/ + 256 /*barriers*/ +
                                2 * BN * 4 /*bias, scale*/;
@@ -376,6 +378,7 @@ template <int BN, int MODE, int EPI, int MC>
 __global__ void __launch_bounds__(TcThreads<MODE, EPI>::value, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
   using Cfg = TcCfg<BN, MODE>;
+  static_assert(Cfg::kPatchBytes > 0 || (EPI == 1 && MODE == kModeX3), "this epilogue needs its staging block");
   constexpr int NS = Cfg::kStages, NP = Cfg::kPlanes;
   const uint32_t crank = MC ? ptx::cluster_ctarank() : 0u;
   extern __shared__ unsigned char smem_dyn[];
