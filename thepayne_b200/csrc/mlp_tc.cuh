@@ -417,6 +417,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   if (MC) ptx::cluster_sync_all();          // the peer's barriers must exist before anything is multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no
+  // global data, so it may run while the previous layer's grid drains; from here on the previous
+  // grid must have completed.  The next layer is released right away -- it parks at this same point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer: stage = [A planes][B planes]
@@ -842,6 +847,9 @@ encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __
                         __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldp, int B) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // lets the first tensor-core layer (launched with programmatic stream serialization) get resident and
+  // run its prologue now; it still waits for this grid to finish before touching the planes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p >= B) return;
   float mine = 0.f;
   if (lane < E.D_in) {
@@ -997,6 +1005,13 @@ inline bool tc_multicast_enabled() {
   return v != 0;
 }
 
+// PAYNE_GEMM_PDL=0 switches programmatic dependent launch of the layer chain off.
+inline bool tc_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PAYNE_GEMM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <int BN, int MODE, int EPI, int MC>
 inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                           void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
@@ -1045,7 +1060,14 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
   } else {
     const int tiles = num_m * num_n;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    tc_gemm_kernel<BN, MODE, EPI, MC><<<grid, TcThreads<MODE, EPI>::value, Cfg::kSmem, st>>>(T, G);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TcThreads<MODE, EPI>::value); cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = tc_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, EPI, MC>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
