@@ -162,6 +162,7 @@ int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
  * see payne_ctx_last_ms), "fast_tail" (0 forces the general-grid tail), "debug_skip" (profiling aid:
  * switches phases of the fused tail off, results are then meaningless; see csrc/tail.cuh).
  * Environment, read once: PAYNE_ROT_WINDOW=0 (no shared-memory slice of the rotation-kernel table),
+ * PAYNE_GEMM_PDL=0 (no programmatic dependent launch along the layer chain),
  * PAYNE_GEMM_MULTICAST=1 / PAYNE_GEMM_2SM=1|2 (experimental GEMM variants: weight multicast, cta_group::2
  * pair tiles 256x128 / 256x256; bit-exact, slower or equal). */
 int payne_ctx_set(PayneCtx* ctx, const char* key, int64_t value);
