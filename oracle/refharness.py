@@ -7,8 +7,10 @@ register *shell* packages whose ``__path__`` points into the reference tree (so 
 ``__init__.py`` runs), import the hot-path modules as they are, and inject random-init
 networks into instances made with ``__new__`` (their constructors only read HDF5).
 
-Nothing here is used on the GPU box: ``/root/reference`` does not exist there.  The only
-consumer is ``oracle/make_golden.py``, which writes ``tests/golden/*.npz``.
+``/root/reference`` does not exist on the GPU box; there the same unmodified files are found
+under ``oracle/_ref`` (staged byte for byte by ``oracle/make_ref.py`` in the build container,
+git-ignored, shipped with the gpurun snapshot).  Consumers: ``oracle/make_golden.py`` (writes
+``tests/golden/*.npz``), ``bench.py --impl reference`` and bench.py's ``cpu_baseline`` leg.
 """
 from __future__ import annotations
 
@@ -20,7 +22,9 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get('PAYNE_REFERENCE', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+REF_ROOT = os.environ.get('PAYNE_REFERENCE') or (
+    '/root/reference' if os.path.isdir('/root/reference/Payne') else _STAGED)
 
 
 def available():

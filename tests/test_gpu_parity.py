@@ -5,11 +5,10 @@ Bars (BASELINE.json north_star): per-pixel model flux within 1e-5 relative and |
 evaluation for the fp32-equivalent modes ("parity" = tcgen05 exact-accumulation split, "simt" =
 CUDA-core fp32).  The TF32 modes are stated separately, as the north star allows.
 
-lnL tolerance used here:  max(1e-3, 1e-8 * |lnL|): the flat 1e-3 for every point within 1e5 of the
-likelihood peak; beyond that (prior-box corners of the joint spectrum+photometry cases, |lnL| up
-to 1e6) a relative 1e-8, because there even the reference's own fp32 emulator is reproducible to
-only ~3e-4 (oracle batch-1 vs exact arithmetic) and 1e-3 is 1e-9 of the value.  Measured: parity
-mode <= 8.4e-4 on every golden row; flux errors <= 6e-8, 150x inside the 1e-5 bar.
+lnL tolerance used here: parity mode is held to the FLAT north-star bar, |dlnL| <= 1e-3 on every golden
+row (up to |lnL| = 1e6 at the prior-box corners of the joint cases).  The CUDA-core cross-check mode
+"simt" (sequential fp32 accumulation, like a naive reference) gets max(2e-3, 2e-8 |lnL|).
+Flux errors are <= 6e-8, 150x inside the 1e-5 bar.
 """
 import numpy as np
 import pytest
@@ -22,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 # precision -> (flux rel bar, lnL abs bar, lnL rel bar)
 BARS = {
-    'parity': (1e-5, 1e-3, 1e-8),      # tcgen05 exact-accumulation bf16x3 MLP  (the default)
+    'parity': (1e-5, 1e-3, 0.0),       # tcgen05 exact-accumulation bf16x3 MLP  (the default): flat bar
     'simt': (1e-5, 2e-3, 2e-8),        # CUDA-core fp32 MLP (sequential fp32 accumulation; cross-check mode)
     '3xtf32': (1e-5, 3e-2, 1.5e-6),    # tcgen05 3xTF32: accumulator truncation bias -> NOT lnL-parity
     'tf32': (3e-4, 0.5, 5e-5),         # tcgen05 1xTF32 -- fast mode, NOT a parity mode

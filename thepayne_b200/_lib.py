@@ -11,6 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpayne_b200.so')
 
+ABI_VERSION = 2          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
 NPAR = 13
 MAX_POLY = 16
 PAR_INDEX = {
@@ -71,6 +72,10 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     lib.payne_abi_version.restype = C.c_int
+    got = lib.payne_abi_version()
+    if got != ABI_VERSION:
+        raise PayneError('%s has ABI version %d, these bindings expect %d: rebuild it with '
+                         '`python -m thepayne_b200.build`' % (LIB_PATH, got, ABI_VERSION))
     lib.payne_last_error.restype = C.c_char_p
     lib.payne_ctx_create.restype = C.c_int
     lib.payne_ctx_create.argtypes = [C.POINTER(PayneSpecNet), C.POINTER(PaynePhotNet), C.POINTER(PayneObs),

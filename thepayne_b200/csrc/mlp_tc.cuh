@@ -249,6 +249,7 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
 #define PAYNE_GEMM_2SM_DEFAULT 0
 #endif
 constexpr int kTcThreads = 256;
+constexpr int kX3MaxK = 512;    // widest contraction the exact-accumulation split covers (see header)
 // Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get four
 // groups of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and took more
 // than half of the kernel; each group takes 16 of the tile's 64 columns.
@@ -1039,11 +1040,14 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
       cache->variant = kVariant;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in above 48 KB is a per-device attribute of the function: one flag per device ordinal
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PAYNE_E_CUDA;
+  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::kSmem) != cudaSuccess) return PAYNE_E_CUDA;
-    attr_set = true;
+    if (dev < 64) attr_set |= 1ull << dev;
   }
   TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K};
   const int num_m = (M + kBM - 1) / kBM, num_n = (W.N + BN - 1) / BN;
@@ -1092,11 +1096,13 @@ inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float
     if (make_tmap(&T.b[p], W.xplane[p], W.N, K, W.Kp, C2::BNH, 2)) return PAYNE_E_CUDA;
   }
   if (int rc = make_tmap_out(&T.c, out0, mrows, W.N, ldc)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PAYNE_E_CUDA;
+  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
     if (cudaFuncSetAttribute(tc_gemm2_kernel<0, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem) != cudaSuccess)
       return PAYNE_E_CUDA;
-    attr_set = true;
+    if (dev < 64) attr_set |= 1ull << dev;
   }
   TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K};
   const int pair_tiles = ((M + 255) / 256) * ((W.N + BN - 1) / BN);
@@ -1167,6 +1173,10 @@ inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* di
                          TcMapCache* caches = nullptr, long long out_rows = 0) {
   for (int k = 1; k < 6; ++k)
     if (!tcw[k].plane[0]) return PAYNE_E_UNSUPPORTED;
+  // exactness of the leading product sum (header): K * 2^8 * 2^7 <= 2^24 needs K <= 512
+  if (prec == PAYNE_PREC_PARITY)
+    for (int k = 1; k < 6; ++k)
+      if (dims_in[k] > kX3MaxK) return PAYNE_E_UNSUPPORTED;
   switch (prec) {
     case PAYNE_PREC_PARITY:
       return tc_run_layers_mode<kModeX3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,

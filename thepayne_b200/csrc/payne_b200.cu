@@ -124,6 +124,9 @@ struct PayneCtx {
   payne::TcMapCache mapc[6];       // tensor maps per layer, valid while the workspace stays put
   cudaStream_t side = nullptr;     // per-point tail setup runs here, beside the emulator GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_done = nullptr;   // end of the last call that used the workspace
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
   PayneLayout lay{};
   // spectrum emulator
   bool has_spec = false;
@@ -166,6 +169,29 @@ struct PayneCtx {
 };
 
 namespace {
+
+// Entry points select the context's device and put the caller's device back on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+// The workspace (flux slab, activation planes, per-point records) is shared by every entry point, and
+// entry points may be given different streams: a call on another stream than the previous one first
+// waits for the previous call's work.
+int order_after_previous(PayneCtx* c, cudaStream_t st) {
+  if (c->has_last && c->last_stream != st) CU_TRY(cudaStreamWaitEvent(st, c->ev_done, 0));
+  return PAYNE_OK;
+}
+int mark_done(PayneCtx* c, cudaStream_t st) {
+  CU_TRY(cudaEventRecord(c->ev_done, st));
+  c->last_stream = st; c->has_last = true;
+  return PAYNE_OK;
+}
 
 template <class T>
 int upload_owned(PayneCtx* c, T** dst, const T* src, size_t n) {
@@ -230,6 +256,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   T.lnw0 = std::log(w[0]);
   T.inv_dlnw = (double)(n - 1) / (std::log(w[n - 1]) - std::log(w[0]));
   T.sigma_in = kCkms / s->resolution;
+  T.inst_scale = kFwhmFit;
   // log-uniform check (informational; enables the analytic regrid fast path later)
   double maxdev = 0.0;
   for (int i = 0; i < n; ++i)
@@ -450,6 +477,13 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     return fail(PAYNE_E_UNSUPPORTED,
                 "a 65536-point transform needs the log-uniform fast tail (emulator grid is not log-uniform)");
   }
+  // Parity mode's "the tensor core never rounds the leading product sum" holds for contractions up to
+  // 512 wide (mlp_tc.cuh header); wider hidden layers must use the CUDA-core fp32 mode.
+  if (!c->legacy && c->lay.precision == PAYNE_PREC_PARITY)
+    for (int k = 1; k < 6; ++k)
+      if (din[k] > payne::kX3MaxK)
+        return fail(PAYNE_E_UNSUPPORTED, "parity precision supports hidden widths up to 512 (layer " + std::to_string(k + 1) +
+                    " contracts over " + std::to_string(din[k]) + "); use precision 'simt'");
   // tensor-core operand copies of the weights (sigmoid LinNet only)
   for (int k = 1; k < 6 && !c->legacy; ++k) {
     rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
@@ -577,8 +611,9 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
   using namespace payne;
   if (B <= 0) return PAYNE_OK;
   if (ld < c->lay.ndim) return fail(PAYNE_E_INVALID, "ld < ndim");
-  CU_TRY(cudaSetDevice(c->device));
   int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  rc = order_after_previous(c, st);
   if (rc) return rc;
   if (c->timing) { c->ms_acc[0] = c->ms_acc[1] = c->ms_acc[2] = 0; c->ms_valid = false; c->pending.clear(); }
   for (long long p0 = 0; p0 < B; p0 += c->slab) {
@@ -652,7 +687,7 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
     if (c->timing) { CU_TRY(cudaEventRecord(evs[3], st)); c->pending.push_back(evs); }
     CU_TRY(cudaGetLastError());
   }
-  return PAYNE_OK;
+  return mark_done(c, st);
 }
 
 }  // namespace
@@ -674,7 +709,7 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(PAYNE_E_CUDA, "no CUDA device: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(PAYNE_E_INVALID, "bad device ordinal");
-  CU_TRY(cudaSetDevice(device));
+  DeviceGuard dg(device);
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(PAYNE_E_UNSUPPORTED, "built for sm_100a (B200) only");
@@ -685,7 +720,8 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(PAYNE_E_CUDA, "stream");
   if (!rc && (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
               cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-              cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess))
+              cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess))
     rc = fail(PAYNE_E_CUDA, "side stream");
   if (!rc && cudaMalloc((void**)&c->status, sizeof(int)) != cudaSuccess) rc = fail(PAYNE_E_NOMEM, "status");
   if (!rc) cudaMemset(c->status, 0, sizeof(int));
@@ -698,7 +734,7 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
 
 void payne_ctx_destroy(PayneCtx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard dg(c->device);
   cudaDeviceSynchronize();
   for (void* p : c->owned) cudaFree(p);
   auto drop = [&](void* p) { if (p) cudaFree(p); };
@@ -713,6 +749,7 @@ void payne_ctx_destroy(PayneCtx* c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   delete c;
 }
 
@@ -721,6 +758,7 @@ int payne_lnlike_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t 
   if (!c) return fail(PAYNE_E_INVALID, "null argument");
   if (B == 0) return PAYNE_OK;                       // an empty batch may come with null buffers
   if (!theta_dev || !lnl_dev) return fail(PAYNE_E_INVALID, "null argument");
+  DeviceGuard dg(c->device);
   return run_batch(c, theta_dev, B, ld, nullptr, nullptr, lnl_dev, (cudaStream_t)stream);
 }
 
@@ -729,6 +767,7 @@ int payne_model_batch(PayneCtx* c, const double* theta_dev, int64_t B, int64_t l
   if (!c) return fail(PAYNE_E_INVALID, "null argument");
   if (B == 0) return PAYNE_OK;
   if (!theta_dev) return fail(PAYNE_E_INVALID, "null argument");
+  DeviceGuard dg(c->device);
   return run_batch(c, theta_dev, B, ld, flux_dev, mags_dev, lnl_dev, (cudaStream_t)stream);
 }
 
@@ -737,7 +776,7 @@ int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, in
   if (B == 0) return PAYNE_OK;
   if (!theta_host || !lnl_host) return fail(PAYNE_E_INVALID, "null argument");
   if (B <= 0) return PAYNE_OK;
-  CU_TRY(cudaSetDevice(c->device));
+  DeviceGuard dg(c->device);
   if (B > c->stage_cap || ld != c->stage_ld) {
     if (c->theta_pin) cudaFreeHost(c->theta_pin);
     if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
@@ -771,8 +810,10 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
   if (!c->legacy && c->lay.precision != PAYNE_PREC_SIMT_FP32 && ((ldy & 3) || ((uintptr_t)y_dev & 15)))
     return fail(PAYNE_E_INVALID, "y_dev must be 16-byte aligned with ldy a multiple of 4 (TMA store)");
   if (B <= 0) return PAYNE_OK;
-  CU_TRY(cudaSetDevice(c->device));
+  DeviceGuard dg(c->device);
   int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  rc = order_after_previous(c, (cudaStream_t)stream);
   if (rc) return rc;
   payne::EncodeParams E = c->enc;
   for (int i = 0; i < E.D_in; ++i) E.col[i] = i;
@@ -782,7 +823,7 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
     rc = run_mlp(c, E, x_dev + p0 * c->D_in, c->D_in, nb, y_dev + p0 * ldy, ldy, false, &isd, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  return PAYNE_OK;
+  return mark_done(c, (cudaStream_t)stream);
 }
 
 int64_t payne_ctx_query(PayneCtx* c, const char* key) {
@@ -800,7 +841,7 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "precision") return c->lay.precision;
   if (k == "status") {
     int v = 0;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaDeviceSynchronize();
     cudaMemcpy(&v, c->status, sizeof(int), cudaMemcpyDeviceToHost);
     return v;
@@ -813,6 +854,10 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   std::string k(key);
   if (k == "precision") {
     if (value < 0 || value > 4 || value == PAYNE_PREC_BF16) return fail(PAYNE_E_INVALID, "unknown precision");
+    if (value == PAYNE_PREC_PARITY && c->has_spec && !c->legacy)
+      for (int k = 1; k < 6; ++k)
+        if (c->dims_in[k] > payne::kX3MaxK)
+          return fail(PAYNE_E_UNSUPPORTED, "parity precision supports hidden widths up to 512");
     c->lay.precision = (int)value;
     return PAYNE_OK;
   }
@@ -823,7 +868,10 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   }
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
-  if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }   // profiling aid, see tail.cuh
+  if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }
+  // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
+  // resolution the likelihood samples (genmod.py:82-85)
+  if (k == "inst_r_is_sigma") { c->tail.inst_scale = value ? 1.0 : payne::kFwhmFit; return PAYNE_OK; }   // profiling aid, see tail.cuh
   return fail(PAYNE_E_INVALID, "unknown key " + k);
 }
 

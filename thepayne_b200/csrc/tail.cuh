@@ -74,6 +74,7 @@ struct TailParams {
   double* model_out;        // [B, n_obs] or null
   int* status;              // device flag: bit0 = a point needed a larger FFT than the carve-out
   int B;
+  double inst_scale;        // Inst_R -> sigma-resolution: 2.355 (genmod.py:83, FWHM given) or 1 (getspec callers)
   int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
                             // bit3 the regrid back, bit4 the final pass; results are garbage
 };
@@ -190,7 +191,7 @@ __device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S)
   if (!(S.D > 0.0)) S.bad = 1;
   S.lnD = log(S.D);
   for (int k = 0; k < P.n_poly; ++k) S.poly[k] = th[P.poly_col[k]];
-  const double Rs = kFwhmFit * instR;             // genmod.py:83
+  const double Rs = P.inst_scale * instR;         // genmod.py:83 (inst_scale = 2.355) or predictspec.py:255-263 (1)
   S.use_inst = (Rs > 0.0);                        // predictspec.py:257 (false for NaN)
   S.log2N2 = 0; S.i0 = 0; S.i1 = P.n - 1;
   if (!S.use_inst || S.bad) return;

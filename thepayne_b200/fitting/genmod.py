@@ -34,11 +34,19 @@ class GenMod(object):
             raise NotImplementedError('carbon_bool is hard-wired off in the reference (fitstar.py:150-154)')
         pars = [float(p) for p in pars]
         polycoef = pars[8:] if modpoly else []
+        if outwave is None:
+            # genmod.py:87-100 + predictspec.py:243-294: the Doppler-shifted native grid, flux not resampled
+            inst = pars[7] * 2.355 if np.isfinite(pars[7]) else pars[7]
+            wave, flux = self.PP.getspec(Teff=pars[0], logg=pars[1], feh=pars[2], afe=pars[3], rad_vel=pars[4],
+                                         rot_vel=pars[5], vmic=pars[6], inst_R=inst, outwave=None)
+            if modpoly:
+                from .fitutils import polycalc
+                flux = flux * polycalc(polycoef, wave)
+            return wave, flux
         eng = self.PP.anns.engine_for(outwave, npoly=len(polycoef))
         row = np.array([pars[:8] + list(polycoef)], dtype=np.float64)
         flux, _, _ = eng.model_batch(row, want_mags=False)
-        wave = self.PP.anns.wavelength if outwave is None else outwave
-        return wave, flux[0].cpu().numpy()
+        return outwave, flux[0].cpu().numpy()
 
     def genphot(self, pars, rvfree=False, verbose=False):   # genmod.py:110-155
         if rvfree:

@@ -1,20 +1,31 @@
 """High-extinction (Av >= 5) analytic extension of the bolometric corrections.
 
 Mirror of ``Payne/predict/highred.py:4-25``: per band ``BC0 - (a1 + b1*Av*(a2 + b2*Rv + c2*Rv**2))``.
-The per-band coefficient table of the reference (highred.py:29-169) is data, not code: it is
-read from a whitespace table (``filter a1 b1 a2 b2 c2``) so it can be exported from a
-reference checkout with ``highAv.export_reference_table`` and dropped next to the ANNs.
-Bands missing from the table get NaN coefficients, as in the reference (highred.py:14-15).
+The per-band coefficient table of the reference (highred.py:29-169) is data, not code: it ships
+as ``thepayne_b200/data/highav_coeffs.txt`` (``filter a1 b1 a2 b2 c2``), written from a reference
+checkout by ``tools/export_highav.py``; ``PAYNE_HIAV_TABLE`` / ``table=`` add or override rows.
+Bands missing from the table get NaN coefficients, as in the reference (highred.py:14-15) -- with
+a warning, because every magnitude of such a band turns NaN as soon as a point has Av >= 5.
 """
 from __future__ import annotations
 
 import os
+import warnings
 
 import numpy as np
 
-from ..synth import _HIAV_SYNTH
-
 _TABLE_ENV = 'PAYNE_HIAV_TABLE'
+TABLE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data', 'highav_coeffs.txt')
+_cache = {}
+
+
+def reference_table():
+    """{band: (a1, b1, a2, b2, c2)} of the shipped table (all bands of highred.py:29-169)."""
+    if 'tab' not in _cache:
+        if not os.path.exists(TABLE_PATH):
+            raise IOError('%s is missing: run tools/export_highav.py against a reference checkout' % TABLE_PATH)
+        _cache['tab'] = _read_table(TABLE_PATH)
+    return dict(_cache['tab'])
 
 
 def _read_table(path):
@@ -29,10 +40,14 @@ def _read_table(path):
 
 class highAv(object):
     def __init__(self, filters, table=None):
-        tab = dict(_HIAV_SYNTH)
+        tab = reference_table()
         path = table or os.environ.get(_TABLE_ENV)
         if path:
             tab.update(_read_table(path))
+        missing = [ff for ff in filters if ff not in tab]
+        if missing:
+            warnings.warn('no high-Av coefficients for %s: their magnitudes are NaN for Av >= 5 '
+                          '(as in the reference, highred.py:14-15)' % ', '.join(missing))
         self.Avlist = [list(tab[ff]) if ff in tab else [np.nan] * 5 for ff in filters]
 
     def getAvaprox(self, Av, Rv, pars):

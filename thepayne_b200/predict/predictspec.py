@@ -14,7 +14,6 @@ from ..synth import SpecNet
 
 speedoflight = 299792.458
 _FULL = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R']
-_FWHM = 2.355   # the kernel applies genmod.py:83's factor itself
 
 
 def _as_specnet(nnpath, NNtype='LinNet'):
@@ -44,10 +43,12 @@ class ANN(object):
         self.precision = kwargs.get('precision', 'parity')
         self._engines = {}
 
-    def engine_for(self, outwave=None, npoly=0):
-        """Engine whose observed grid is ``outwave`` (None -> the emulator's own grid)."""
+    def engine_for(self, outwave=None, npoly=0, inst_sigma=False):
+        """Engine whose observed grid is ``outwave`` (None -> the emulator's own grid).
+        ``inst_sigma``: the Inst_R column is the sigma-resolution ``getspec`` takes (predictspec.py:255-263),
+        not the FWHM resolution ``GenMod.genspec`` multiplies by 2.355 (genmod.py:82-85)."""
         ow = self.wavelength if outwave is None else np.ascontiguousarray(outwave, dtype=np.float64)
-        key = (ow.tobytes(), npoly)
+        key = (ow.tobytes(), npoly, bool(inst_sigma))
         if key not in self._engines:
             if len(self._engines) > 8:
                 self._engines.pop(next(iter(self._engines))).close()
@@ -56,6 +57,8 @@ class ANN(object):
             self._engines[key] = Engine(spec=self.model, obs_wave=ow, obs_flux=one, obs_eflux=one,
                                         fitpars_i=fit, runbools=(True, False, npoly > 0, False, False),
                                         precision=self.precision)
+            if inst_sigma:
+                self._engines[key].set('inst_r_is_sigma', 1)
         return self._engines[key]
 
     def eval(self, x):
@@ -113,14 +116,14 @@ class PayneSpecPredict(object):
         if outwave is None:
             # no resampling of the wavelength axis: the reference returns the (shifted) native grid
             grid = modwave * (1.0 + (rad / speedoflight)) if rad != 0.0 else modwave
-            eng = self.anns.engine_for(grid)
+            eng = self.anns.engine_for(grid, inst_sigma=True)
         else:
             outwave = np.array(outwave)
             grid = outwave
-            eng = self.anns.engine_for(outwave)
+            eng = self.anns.engine_for(outwave, inst_sigma=True)
         d = self.inputdict
         row = np.array([[d['teff'], d['logg'], d['feh'], d['afe'], rad, rot, d['vmic'],
-                         inst / _FWHM if inst > 0.0 else np.nan]], dtype=np.float64)
+                         inst if inst > 0.0 else np.nan]], dtype=np.float64)
         flux, _, _ = eng.model_batch(row, want_mags=False)
         return grid, flux[0].cpu().numpy()
 
@@ -133,6 +136,6 @@ class PayneSpecPredict(object):
         th[:, 4], th[:, 5] = rad_vel, rot_vel
         if vmic is not None:
             th[:, 6] = vmic
-        th[:, 7] = np.asarray(inst_R, dtype=np.float64) / _FWHM
-        flux, _, _ = self.anns.engine_for(outwave).model_batch(th, want_mags=False)
+        th[:, 7] = np.asarray(inst_R, dtype=np.float64)
+        flux, _, _ = self.anns.engine_for(outwave, inst_sigma=True).model_batch(th, want_mags=False)
         return flux

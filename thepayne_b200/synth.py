@@ -122,27 +122,6 @@ def make_specnet(D_in, H, wave, resolution, seed=0, out_scale=0.3, out_bias=1.0,
         resolution=float(resolution), inlabels=labels, nntype=nntype)
 
 
-# A few rows of the reference's high-Av table (highred.py:29-169) are needed by the
-# Av>=5 branch. Only the bands used by the synthetic configs are listed; real runs get
-# the table through ``thepayne_b200.predict.highred.highAv``.
-_HIAV_SYNTH = {
-    '2MASS_H': (0.005144743611935593, -0.08825804196965176, -4.459177107383617,
-                1.3211410779710815, -0.126433306346117),
-    '2MASS_J': (0.005440139230159183, -0.23220874507059025, -2.9976731151290528,
-                0.9214433960096281, -0.09029532801360127),
-    '2MASS_Ks': (0.002080727108144654, -0.12514127988737334, -1.9538876061688348,
-                 0.594465850222952, -0.05813606611952772),
-    'Bessell_B': (0.024026662865963402, -0.32742482625331054, -5.0101650007947285,
-                  0.5122639727388698, -0.046816477985748846),
-    'Bessell_I': (0.00608032720073613, -0.3649990760906186, -3.0372850482808205,
-                  0.7326438817961413, -0.07162932318768075),
-    'Bessell_R': (0.03687149748433364, -0.14548310063602554, -6.847739151725625,
-                  0.764136666546879, -0.07078756454293482),
-    'Bessell_V': (0.012743463425026642, -0.3196046543375275, -3.179566963010358,
-                  0.026123205537807507, -0.0003117061154394677),
-}
-
-
 def make_photnet(bands, H=128, seed=7):
     """Random-init per-band ``Net(6,H,1)`` (``photANN.py:21-26``), built band by band
     in list order so the reference harness can recreate the same modules."""
@@ -157,7 +136,9 @@ def make_photnet(bands, H=128, seed=7):
         w3.append(l3.weight.detach().numpy().copy()); b3.append(l3.bias.detach().numpy().copy())
     xmin = np.array([2500.0, -1.0, -4.0, -0.2, 0.0, 2.0])
     xmax = np.array([50000.0, 5.5, 0.5, 0.6, 5.0, 5.0])
-    hiav = np.array([_HIAV_SYNTH.get(b, (np.nan,) * 5) for b in bands], dtype=np.float64)
+    from .predict.highred import reference_table
+    tab = reference_table()
+    hiav = np.array([tab.get(b, (np.nan,) * 5) for b in bands], dtype=np.float64)
     return PhotNet(list(bands), np.array(w1), np.array(b1), np.array(w2), np.array(b2),
                    np.array(w3), np.array(b3), xmin, xmax, hiav)
 
