@@ -8,9 +8,12 @@ batch of B synthetic live points of config C2 (LinNet 4-256-256-
 UVES-range mock, n_obs 7000).  N>1: one process per GPU (torchrun), B points per GPU (weak
 scaling), replicated weights, one NCCL all-gather of the lnL vector per step.
 
-`--impl reference` times the CPU restatement of the reference's per-point path (the oracle
-port: oracle/payne_oracle.py, scalar `lnlikefn` incl. the reference's Python chi2 loop) on
-all host cores.  The reference itself is pure Python and cannot travel to the GPU box.
+`--impl reference` times the reference's own likelihood path on all host cores: the UNMODIFIED
+reference files staged under oracle/_ref (oracle/make_ref.py copies them byte for byte in the build
+container; the directory is git-ignored and ships with the gpurun snapshot), driven through
+oracle/refharness.py exactly as the golden fixtures were minted -- kind "reference".  Only when that
+directory is absent does the arm fall back to the oracle port (kind "port").  Same workload string,
+same theta seed and the same points per step as the CUDA arm.
 """
 from __future__ import annotations
 
@@ -42,25 +45,47 @@ def load_peaks():
 _W = {}
 
 
-def _cpu_init(cfg):
-    import torch
-    torch.set_num_threads(1)
+def reference_kind():
+    """'reference' when the unmodified reference files are present (oracle/_ref or /root/reference)."""
+    from oracle import refharness
+    return 'reference' if refharness.available() else 'port'
+
+
+def make_cpu_like(cfg, kind, vector_chi2=False):
+    """Scalar ``lnlikefn(theta_row) -> float`` of the reference (or of the oracle port)."""
+    if kind == 'reference':
+        import warnings
+        warnings.filterwarnings('ignore')
+        from oracle import refharness
+        like = refharness.build_likelihood(cfg)
+        if vector_chi2:
+            refharness.vectorise_chi2(like)
+        return like.lnlikefn
     from oracle import payne_oracle as O
-    _W['L'] = O.OracleLikelihood(cfg)
+    return O.OracleLikelihood(cfg).lnlikefn
+
+
+def _cpu_init(cfg, kind, threads):
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    _W['fn'] = make_cpu_like(cfg, kind)
 
 
 def _cpu_eval(rows):
-    L = _W['L']
-    return [float(L.lnlikefn(r)) for r in rows]
+    fn = _W['fn']
+    return [float(fn(r)) for r in rows]
 
 
 class CpuPool:
-    """All host cores, one single-threaded oracle per process (reference: one vector per call)."""
+    """All host cores, one single-threaded likelihood object per process (the reference evaluates
+    one parameter vector per call)."""
 
-    def __init__(self, cfg, cores=None):
+    def __init__(self, cfg, cores=None, kind='reference'):
         import multiprocessing as mp
         self.cores = cores or os.cpu_count() or 1
-        self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_cpu_init, initargs=(cfg,))
+        self.kind = kind
+        self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_cpu_init, initargs=(cfg, kind, 1))
 
     def run(self, theta):
         chunks = [c for c in np.array_split(theta, self.cores * 2) if len(c)]
@@ -72,6 +97,35 @@ class CpuPool:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def single_process_lines(cfg, theta, kind, seconds=4.0):
+    """SURVEY §8d / BASELINE.md §3: one process with 1 thread, one process with the default thread count,
+    and the vectorised-chi2 variant (likelihood.py:95-97 is a Python generator, ~40 % of the reference)."""
+    import torch
+    out = {}
+    default_threads = torch.get_num_threads()
+
+    def rate(fn, n_threads):
+        torch.set_num_threads(n_threads)
+        for r in theta[:3]:
+            fn(r)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds and n < len(theta):
+            fn(theta[n])
+            n += 1
+        return n / (time.perf_counter() - t0), n
+    fn = make_cpu_like(cfg, kind)
+    v, n = rate(fn, 1)
+    out['one_process_1_thread'] = {'value': v, 'unit': UNIT, 'points': n}
+    v, n = rate(fn, default_threads)
+    out['one_process_default_threads'] = {'value': v, 'unit': UNIT, 'points': n, 'threads': default_threads}
+    if kind == 'reference':
+        fnv = make_cpu_like(cfg, kind, vector_chi2=True)
+        v, n = rate(fnv, 1)
+        out['one_process_1_thread_vectorised_chi2'] = {'value': v, 'unit': UNIT, 'points': n}
+    torch.set_num_threads(default_threads)
+    return out
 
 
 # --------------------------------------------------------------------------- clocks
@@ -130,6 +184,61 @@ def build_c2_on_gpu(precision):
     return synth.config_c2(model_fn)
 
 
+def bench_config(B, D_out, n_obs):
+    """The `config` object both arms print (so the driver sees the same workload on both)."""
+    return {'workload': 'C2-uves: LinNet 4-256-256-256-%d random-init, n_obs %d, FFT 16384, theta seed 1234' % (D_out, n_obs),
+            'points_per_gpu': B,
+            'l2': 'per-step working set (flux slab %.0f MB) exceeds the 126 MB L2; no explicit flush'
+                  % (B * D_out * 4 / 1e6)}
+
+
+def other_configs(precision):
+    """Device-resident throughput of the other BASELINE.json configs on one GPU (few steps each)."""
+    import torch
+    from thepayne_b200 import synth
+    from thepayne_b200.engine import engine_from_config
+    out = {}
+
+    def gpu_model_fn(cfg, theta):
+        n = len(cfg.obs_wave)
+        cfg.obs_flux, cfg.obs_eflux = np.ones(n), np.ones(n)
+        if cfg.phot is not None:
+            cfg.obs_phot = {b: [0.0, 1.0] for b in cfg.phot.bands}
+        eng = engine_from_config(cfg, precision=precision)
+        fl, mg, _ = eng.model_batch(torch.from_numpy(np.ascontiguousarray(theta)).cuda())
+        r = (fl.cpu().numpy(), None if mg is None else mg.cpu().numpy())
+        eng.close()
+        return r
+    for key, builder, B, steps, what in [
+            ('c3_joint', synth.config_c3, 16384, 5, 'C3: C2 + 7-band photometry (SED nets H=128), 16384 points'),
+            ('c4_monolithic', synth.config_c4, 4096, 3,
+             'C4 (i): LinNet 5-512-512-512-51784, 65536-point transforms, n_obs 25000, order-4 continuum, Vrot<=100; '
+             '4096-point slabs of the 64k-point batch')]:
+        try:
+            cfg = builder(gpu_model_fn)
+            eng = engine_from_config(cfg, precision=precision)
+            eng.set('max_batch', 8192 if key == 'c3_joint' else 4096)
+            th = torch.from_numpy(np.ascontiguousarray(cfg.draw(B, seed=99))).cuda()
+            for _ in range(2):
+                o = eng.lnlike_batch(th)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = eng.lnlike_batch(th)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[key] = {'workload': what, 'points': B, 'ms_per_step': ms, 'value': B / (ms * 1e-3), 'unit': UNIT,
+                        'finite_lnl': int(torch.isfinite(o).sum().item())}
+            eng.close()
+            del th, o
+            torch.cuda.empty_cache()
+        except Exception as e:                      # an extra line must never cost the headline
+            out[key] = {'error': str(e)[:200]}
+    return out
+
+
 def mlp_flops(cfg):
     dims = [w.shape for w in cfg.spec.weights]
     return 2.0 * sum(o * i for o, i in dims)
@@ -142,27 +251,39 @@ def run_reference(args):
         return
     from oracle import payne_oracle as O
     from thepayne_b200 import synth
+    kind = reference_kind()
     cfg = synth.config_c2(O.model_fn)
     cores = os.cpu_count() or 1
-    pool = CpuPool(cfg, cores)
-    S = max(64, 8 * cores)
-    theta = cfg.draw(S * (args.steps + args.warmup), seed=1234)
+    pool = CpuPool(cfg, cores, kind)
+    B = args.batch
+    theta = cfg.draw(B, seed=1234)                 # the CUDA arm's rank-0 batch
+    # Bound the run: a step is the first S points of the B-point batch, S = B when the whole
+    # --steps/--warmup run then stays within ~4 minutes on this host, else the largest multiple of
+    # the core count that does (probe: one round of 4 points per core).
+    pool.run(theta[:cores])
+    _, dt = pool.run(theta[:4 * cores])
+    per_point = dt / (4 * cores)
+    nsteps = args.steps + args.warmup
+    S = B
+    if per_point * B * nsteps > 240.0:
+        S = max(cores, int(240.0 / (per_point * nsteps)) // cores * cores)
     for i in range(args.warmup):
-        pool.run(theta[i * S:(i + 1) * S])
+        pool.run(theta[:S])
     tot = 0.0
-    for i in range(args.warmup, args.warmup + args.steps):
-        _, dt = pool.run(theta[i * S:(i + 1) * S])
+    for i in range(args.steps):
+        _, dt = pool.run(theta[:S])
         tot += dt
     pool.close()
     v = S * args.steps / tot
-    sample = '%d points/step x %d steps of C2 theta (seed 1234), scalar lnlikefn per point' % (S, args.steps)
+    sample = ('%d of the %d points per step x %d steps, scalar lnlikefn per point, %d procs x 1 thread; '
+              'implementation: %s' % (S, B, args.steps, cores,
+                                      'unmodified reference files (oracle/_ref)' if kind == 'reference' else 'oracle port'))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps * (B / S),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32 MLP / fp64 tail',
-        'data': 'synthetic', 'config': {'workload': 'C2-uves: LinNet 4-256-256-256-14172, n_obs 7000',
-                                        'points_per_step': S},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'data': 'synthetic', 'config': bench_config(B, cfg.spec.D_out, len(cfg.obs_wave)),
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -184,7 +305,7 @@ def run_ours(args):
     cfg = build_c2_on_gpu(args.precision)
     eng = engine_from_config(cfg, precision=args.precision)
     eng.set('max_batch', args.slab)
-    theta_h = np.ascontiguousarray(cfg.draw(B, seed=1234 + rank))
+    theta_h = np.ascontiguousarray(cfg.draw(B, seed=1234 + rank))    # rank 0: the reference arm's batch
     theta = torch.from_numpy(theta_h).cuda()
 
     def barrier():
@@ -230,19 +351,64 @@ def run_ours(args):
     mlp_ms /= K
     tail_ms /= K
 
-    # end to end through the host-buffer C-ABI entry (H2D of theta + D2H of lnL inside)
+    # end to end: host theta in, host lnL out, every step.  N = 1: the host-buffer C-ABI entry
+    # (pinned staging + H2D + kernels + D2H inside the library).  N > 1: pinned theta -> H2D -> kernels ->
+    # NCCL all-gather of lnL -> D2H of the gathered vector, i.e. what a sampler on every rank would see.
+    if world == 1:
+        def e2e_step():
+            return eng.lnlike_batch(theta_h)
+    else:
+        theta_pin = torch.from_numpy(theta_h).pin_memory()
+        lnl_pin = torch.empty(world * B, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            th = theta_pin.cuda(non_blocking=True)
+            g = pdist.gather_equal(eng.lnlike_batch(th))
+            lnl_pin.copy_(g, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return lnl_pin.numpy()
     for _ in range(2):
-        eng.lnlike_batch(theta_h)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        lnl_h = eng.lnlike_batch(theta_h)
+        lnl_h = e2e_step()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # C5 (BASELINE config 5): a 2^20-point sweep of the same workload split over the N GPUs (strong
+    # scaling: total work fixed), slabs of 8192 points, one all-gather of the full lnL vector per step
+    c5 = None
+    if not args.no_extra:
+        total = 1 << 20
+        per = total // world
+        th5 = torch.from_numpy(np.ascontiguousarray(cfg.draw(per, seed=777 + rank))).cuda()
+        eng.set('max_batch', 8192)
+
+        def step5():
+            lnl = eng.lnlike_batch(th5)
+            return pdist.gather_equal(lnl) if world > 1 else lnl
+        step5()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            o5 = step5()
+        f1.record()
+        barrier()
+        ms5 = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms5], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms5 = float(t.item())
+        c5 = {'workload': 'C5: 2^20-point sweep of the C2 workload, strong scaling', 'points_total': per * world,
+              'points_per_gpu': per, 'value': per * world * 3 / (ms5 * 1e-3), 'unit': UNIT, 'ms_per_step': ms5 / 3,
+              'finite_lnl': int(torch.isfinite(o5).sum().item())}
+        del th5, o5
+        eng.set('max_batch', args.slab)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -268,14 +434,12 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'fp32 (tcgen05 bf16x3 exact-accumulation MLP, fp32 FFT tail, fp64 chi2)'
         if args.precision == 'parity' else args.precision,
         'data': 'synthetic',
-        'config': {'workload': 'C2-uves: LinNet 4-256-256-256-%d random-init, n_obs %d, FFT 16384' % (D_out, n_obs),
-                   'points_per_gpu': B, 'precision_mode': args.precision,
-                   'l2': 'per-step working set (flux slab %.0f MB) exceeds the 126 MB L2; no explicit flush'
-                         % (B * eng.query('n_ann') * 4 / 1e6),
-                   'finite_lnl': n_finite},
+        'config': bench_config(B, D_out, n_obs), 'precision_mode': args.precision, 'finite_lnl': n_finite,
         'clocks': sampler.summary(),
         'e2e': {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(theta_h.nbytes),
-                'd2h_bytes_per_step': int(lnl_h.nbytes)},
+                'd2h_bytes_per_step': int(lnl_h.nbytes),
+                'path': 'payne_lnlike_batch_host (C ABI, host buffers)' if world == 1 else
+                        'pinned theta -> H2D -> payne_lnlike_batch -> ncclAllGather(lnL) -> D2H'},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'tail_fast_kernel<%d> (+tail_setup_kernel)' % int(np.log2(eng.query('nfft1'))), 'bound': 'hbm', 'achieved': tail_gbs, 'peak': hbm, 'unit': 'GB/s',
                      'frac': tail_gbs / hbm, 'traffic': traffic, 'algorithmic_bytes': tail_bytes, 'peak_source': which, 'ms_per_launch': tail_ms,
@@ -295,7 +459,8 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        pool = CpuPool(cfg, cores)
+        kind = reference_kind()
+        pool = CpuPool(cfg, cores, kind)
         S = max(64, 8 * cores)
         pool.run(theta_h[:min(S, B)])          # warm-up (spawn + first torch call)
         n, tot, dl = 0, 0.0, 0.0
@@ -308,10 +473,18 @@ def run_ours(args):
             n += S
             i += 1
         pool.close()
-        res['cpu_baseline'] = {'value': n / tot, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                               'sample': '%d of the %d timed points, scalar lnlikefn per point, %d procs x 1 thread'
-                                         % (n, B, cores),
+        res['cpu_baseline'] = {'value': n / tot, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                               'per_core': n / tot / cores,
+                               'sample': '%d of the %d timed points, scalar lnlikefn per point, %d procs x 1 thread; %s'
+                                         % (n, B, cores, 'unmodified reference files (oracle/_ref)' if kind == 'reference'
+                                            else 'oracle port'),
                                'max_abs_dlnl_vs_gpu': dl}
+        res['cpu_baseline'].update(single_process_lines(cfg, theta_h, kind, seconds=min(4.0, args.cpu_seconds / 3)))
+    if c5 is not None:
+        res['c5_sweep'] = c5
+    if world == 1 and not args.no_extra:
+        eng.close()
+        res['other_configs'] = other_configs(args.precision)
     print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
@@ -328,6 +501,7 @@ def main():
     ap.add_argument('--precision', default='parity')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the C3/C4/C5 extra lines')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -34,12 +34,37 @@ CASES = {
     # legacy leaky-ReLU emulators: SMLP = torch fp32, 4 layers; YST1 = numpy fp64, 3 layers
     'mini_smlp': (dict(kind='mini', nntype='SMLP'), 12, 12),
     'mini_yst': (dict(kind='mini', nntype='YST1', H=48), 12, 12),
+    # C1: the reference's own demo (demo/runPayne.py:36-143): the spectrum and magnitudes of
+    # demo/demodata.h5 (n_obs 25600, e = flux/25, 27 bands of which two have no high-Av coefficients)
+    # against a random-init emulator of the demo's shape; the fixture carries the observation
+    'c1': (dict(kind='c1'), 8, 1),
 }
+DEMO_H5 = 'demo/demodata.h5'
 
 
-def build(name, model_fn):
+def demo_observation(ref_root):
+    """(obs_wave, obs_flux, {band: [mag, err]}) of the reference's demo file, read without h5py."""
+    import os
+    from thepayne_b200 import h5lite
+    d = h5lite.read(os.path.join(ref_root, DEMO_H5))
+    names = [x.decode('ascii') if isinstance(x, bytes) else str(x) for x in d['phot/filter']]
+    mags = dict(zip(names, d['phot/phot']))
+    return d['spec/wave'], d['spec/flux'], {b: [float(mags[b]), 0.05] for b in synth.C1_BANDS}
+
+
+def build(name, model_fn, data=None):
+    """``data``: for 'c1' the demo observation -- a loaded fixture (tests) or ``demo_observation()``."""
     kw = dict(CASES[name][0])
     kind = kw.pop('kind')
+    if kind == 'c1':
+        if data is None:
+            raise ValueError("case 'c1' needs the demo observation (fixture or demo_observation())")
+        if isinstance(data, tuple):
+            wave, flux, phot = data
+        else:
+            wave, flux = data['obs_wave'], data['obs_flux']
+            phot = {b: [float(v[0]), float(v[1])] for b, v in zip(synth.C1_BANDS, data['obs_phot'])}
+        return synth.config_c1(model_fn, obs_wave=wave, obs_flux=flux, obs_phot=phot, **kw)
     drop = kw.pop('drop', [])
     fixed = kw.pop('fixed', {})
     base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3, 'c4': synth.config_c4}[kind]

@@ -20,7 +20,9 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 def main(names):
     os.makedirs(OUT, exist_ok=True)
     for name in names:
-        cfg = goldens.build(name, refharness.ref_model_fn)
+        # the demo file lives in the reference checkout (not among the staged hot-path files)
+        data = goldens.demo_observation(os.environ.get('PAYNE_REFERENCE_CHECKOUT', '/root/reference')) if name == 'c1' else None
+        cfg = goldens.build(name, refharness.ref_model_fn, data=data)
         th = goldens.thetas(name, cfg)
         nflux = goldens.CASES[name][2]
         lnl = refharness.ref_lnlike(cfg, th)

@@ -246,6 +246,35 @@ def config_c4(model_fn, **kw):
     return build_config('C4-full', model_fn=model_fn, **args)
 
 
+C1_BANDS = ['2MASS_H', '2MASS_J', '2MASS_Ks', 'Bessell_B', 'Bessell_I', 'Bessell_R', 'Bessell_U', 'Bessell_V',
+            'DECam_g', 'DECam_i', 'DECam_r', 'DECam_u', 'DECam_Y', 'DECam_z', 'PS_g', 'PS_i', 'PS_open', 'PS_r',
+            'PS_w', 'PS_y', 'PS_z', 'SDSS_g', 'SDSS_i', 'SDSS_r', 'SDSS_u', 'Tycho_B', 'Tycho_V']
+
+
+def demo_wavegrid(n=25600, w0=5139.250234270761, step=1.0 / 600000.0):
+    """Pixel grid of the reference's demo spectrum (demo/demodata.h5 ``spec/wave``: log-uniform,
+    5139.25-5363.26 A, 25600 pixels) for runs that do not have the file."""
+    return w0 * (1.0 + step) ** np.arange(n)
+
+
+def config_c1(model_fn, obs_wave=None, obs_flux=None, obs_phot=None, **kw):
+    """C1: the reference's mock-Sun demo (demo/runPayne.py:36-143): n_obs 25600 on 5139-5363 A with
+    e = flux/25 (runPayne.py:50), 27 photometric bands, emulator LinNet 4-256-256-256-15675 on
+    5135-5368 A, parameters (Teff, logg, FeH, aFe, Vrad, Vrot, Inst_R, log(A), Av), photscale.
+    ``obs_flux`` / ``obs_phot`` replace the mock observation by the demo file's arrays (the golden
+    fixture does this); without them the observation is a mock at the truth like every other config."""
+    args = dict(ann_range=(5135.0, 5368.0), bands=C1_BANDS, photH=32, snr=25.0,
+                obs_wave=demo_wavegrid() if obs_wave is None else np.asarray(obs_wave, dtype=np.float64))
+    args.update(kw)
+    cfg = build_config('C1-demo', model_fn=model_fn, **args)
+    if obs_flux is not None:
+        cfg.obs_flux = np.asarray(obs_flux, dtype=np.float64)
+        cfg.obs_eflux = cfg.obs_flux / 25.0
+    if obs_phot is not None:
+        cfg.obs_phot = {b: [float(obs_phot[b][0]), float(obs_phot[b][1])] for b in cfg.phot.bands}
+    return cfg
+
+
 def config_mini(model_fn, **kw):
     """Small everything: fast on the CPU oracle; used for golden vectors."""
     args = dict(ann_range=(5140.0, 5190.0), obs_range=(5150.0, 5180.0), n_obs=1500, H=64)
