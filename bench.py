@@ -67,6 +67,7 @@ def make_cpu_like(cfg, kind, vector_chi2=False):
 
 def _cpu_init(cfg, kind, threads):
     import torch
+    assert not torch.cuda.is_available(), 'the CPU arm must not see a GPU (the reference would move its net there)'
     if threads:
         torch.set_num_threads(threads)
     _W['fn'] = make_cpu_like(cfg, kind)
@@ -77,15 +78,39 @@ def _cpu_eval(rows):
     return [float(fn(r)) for r in rows]
 
 
-class CpuPool:
-    """All host cores, one single-threaded likelihood object per process (the reference evaluates
-    one parameter vector per call)."""
+def _cpu_rate(args):
+    """(seconds, vector_chi2) -> (evals/s, points) of one process looping lnlikefn over its rows."""
+    rows, seconds, vector, cfg, kind = args
+    fn = make_cpu_like(cfg, kind, vector_chi2=True) if vector else _W['fn']
+    for r in rows[:3]:
+        fn(r)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and n < len(rows):
+        fn(rows[n])
+        n += 1
+    return n / (time.perf_counter() - t0), n
 
-    def __init__(self, cfg, cores=None, kind='reference'):
+
+class CpuPool:
+    """Host-core worker processes, one likelihood object each (the reference evaluates one parameter
+    vector per call).  The workers are spawned with CUDA hidden: on a GPU host the reference's
+    ``predictspec.py:16-20`` would otherwise put its tensors on the device, and this arm times the
+    reference's CPU path."""
+
+    def __init__(self, cfg, cores=None, kind='reference', threads=1):
         import multiprocessing as mp
         self.cores = cores or os.cpu_count() or 1
         self.kind = kind
-        self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_cpu_init, initargs=(cfg, kind, 1))
+        keep = os.environ.get('CUDA_VISIBLE_DEVICES')
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''
+        try:
+            self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_cpu_init, initargs=(cfg, kind, threads))
+            self.pool.map(_cpu_eval, [[] for _ in range(self.cores)])      # workers are up (env captured)
+        finally:
+            if keep is None:
+                del os.environ['CUDA_VISIBLE_DEVICES']
+            else:
+                os.environ['CUDA_VISIBLE_DEVICES'] = keep
 
     def run(self, theta):
         chunks = [c for c in np.array_split(theta, self.cores * 2) if len(c)]
@@ -100,31 +125,19 @@ class CpuPool:
 
 
 def single_process_lines(cfg, theta, kind, seconds=4.0):
-    """SURVEY §8d / BASELINE.md §3: one process with 1 thread, one process with the default thread count,
-    and the vectorised-chi2 variant (likelihood.py:95-97 is a Python generator, ~40 % of the reference)."""
-    import torch
+    """SURVEY §8d / BASELINE.md §3: one process with 1 thread, one process with torch's default thread
+    count, and the vectorised-chi2 variant (likelihood.py:95-97 is a Python generator, ~40 % of the
+    reference).  Each runs in its own CUDA-blind worker process."""
     out = {}
-    default_threads = torch.get_num_threads()
-
-    def rate(fn, n_threads):
-        torch.set_num_threads(n_threads)
-        for r in theta[:3]:
-            fn(r)
-        n, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < seconds and n < len(theta):
-            fn(theta[n])
-            n += 1
-        return n / (time.perf_counter() - t0), n
-    fn = make_cpu_like(cfg, kind)
-    v, n = rate(fn, 1)
-    out['one_process_1_thread'] = {'value': v, 'unit': UNIT, 'points': n}
-    v, n = rate(fn, default_threads)
-    out['one_process_default_threads'] = {'value': v, 'unit': UNIT, 'points': n, 'threads': default_threads}
-    if kind == 'reference':
-        fnv = make_cpu_like(cfg, kind, vector_chi2=True)
-        v, n = rate(fnv, 1)
-        out['one_process_1_thread_vectorised_chi2'] = {'value': v, 'unit': UNIT, 'points': n}
-    torch.set_num_threads(default_threads)
+    rows = np.ascontiguousarray(theta[:512])
+    for key, threads, vector in [('one_process_1_thread', 1, False), ('one_process_default_threads', None, False),
+                                 ('one_process_1_thread_vectorised_chi2', 1, True)]:
+        if vector and kind != 'reference':
+            continue
+        pool = CpuPool(cfg, 1, kind, threads)
+        v, n = pool.pool.apply(_cpu_rate, ((rows, seconds, vector, cfg, kind),))
+        pool.close()
+        out[key] = {'value': v, 'unit': UNIT, 'points': n}
     return out
 
 
