@@ -121,3 +121,45 @@ def test_standin_nested_sampler_through_the_pool():
                 live[w], lnl[w] = c, l
     assert pool.batches == 7 and pool.points == 64 * 7
     assert lnl.min() > first and np.isfinite(lnl).all()
+
+
+@pytest.mark.gpu
+def test_fitpayne_batched_fit_recovers_the_mock(tmp_path):
+    """``FitPayne.run(inputdict=...)`` (the reference's user entry, fitstar.py:19-217) on a joint
+    spectrum + photometry mock with a continuum polynomial, sampled by the lock-step batched nested
+    sampler: >= 95 % of the likelihood evaluations go through calls of at least ``queue_size`` points,
+    the truth lies within the posterior, and the output file has the reference's layout."""
+    from conftest import load_case
+    from thepayne_b200.fitting.fitstar import FitPayne
+    cfg, g = load_case('mini_joint')
+    Q = 128
+    inputdict = {
+        'spec': {'obs_wave': cfg.obs_wave, 'obs_flux': cfg.obs_flux, 'obs_eflux': cfg.obs_eflux,
+                 'normspec': False, 'convertair': False, 'modpoly': True},
+        'specANNpath': cfg.spec, 'NNtype': 'LinNet',
+        'phot': dict(cfg.obs_phot), 'photANNpath': cfg.phot, 'photscale': True,
+        'sampler': {'samplertype': 'Static', 'samplemethod': 'rwalk', 'npoints': Q, 'walks': 25,
+                    'delta_logz_final': 0.5, 'flushnum': 100, 'seed': 11},
+        'priordict': {p: {'pv_uniform': list(cfg.box[p])} for p in cfg.fitpars_i if not p.startswith('pc_')},
+        'output': str(tmp_path / 'demoout.dat'),
+    }
+    inputdict['priordict']['Inst_R'] = {'pv_tgaussian': [30000.0, 37000.0, 32000.0, 1000.0]}   # demo/runPayne.py:137-139
+    inputdict['priordict']['blaze_coeff'] = [[0.0, 1.0], [0.0, 0.02], [0.0, 0.02]]
+    FS = FitPayne()
+    sampler = FS.run(inputdict=inputdict, verbose=False)
+    assert FS.likeobj.fitpars_i == cfg.fitpars_i
+    r = sampler.results
+    b = r['batch_sizes']
+    assert b.sum() == r['ncall']
+    assert b[b >= Q].sum() / b.sum() >= 0.95, b[b >= Q].sum() / b.sum()
+    assert np.isfinite(r['logz']) and r['niter'] > 10 * Q
+    mean, sd = sampler.posterior_mean_std()
+    z = (mean - cfg.theta_true) / sd
+    assert np.all(sd > 0) and np.all(np.abs(z) < 5.0), dict(zip(cfg.fitpars_i, np.round(z, 2)))
+    # the best point beats the truth's likelihood only by the usual ~ndim/2
+    lnl_true = float(FS.likeobj.lnlike_batch(cfg.theta_true[None, :])[0])
+    assert r['logl'].max() > lnl_true - 1.0 and r['logl'].max() < lnl_true + 40.0
+    rows = open(inputdict['output']).read().strip().split('\n')
+    assert rows[0].split()[:3] == ['Iter', 'Teff', 'log(g)'] and rows[0].split()[-1] == 'delta(log(z))'
+    assert len(rows) == 1 + r['niter'] + Q
+    assert len(rows[1].split()) == 1 + len(cfg.fitpars_i) + 7
