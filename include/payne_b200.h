@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PAYNE_ABI_VERSION 2
+#define PAYNE_ABI_VERSION 3
 
 enum {
   PAYNE_OK = 0,
@@ -79,6 +79,11 @@ enum {
  *   6 (or 0): LinNet  D_in-H1-H1-H2-H2-H3-D_out, sigmoid          (NNmodels.py:140-168)
  *   4       : SMLP    D_in-H1-H2-H3-D_out,      leaky ReLU 0.01   (NNmodels.py:92-115)
  *   3       : YST1    D_in-H1-H2-D_out,         leaky ReLU 0.01   (predict/ystpred.py:18-58)
+ *   4 + SIGMOID + n_groups >= 1 : multi-chunk emulator, n_groups nets Net(D_in,H1,P) of four sigmoid-sigmoid-
+ *             sigmoid-linear layers each covering group_size consecutive pixels (Payne/train/old/
+ *             trainspec_multi.py:29-52); W[0] = [n_groups,H1,D_in], W[1], W[2] = [n_groups,H1,H1], W[3] =
+ *             [D_out,H1] (the chunks' output layers one after another), biases alike; H2 = H3 = H1;
+ *             encode_offset 0 (trainspec_multi.py:56-67).
  * The leaky-ReLU stacks run on the CUDA-core fp32 kernels whatever PayneLayout.precision says
  * (the tensor-core operand slicing needs activations in [0,1)). */
 enum { PAYNE_ACT_SIGMOID = 0, PAYNE_ACT_LEAKY_RELU = 1 };
@@ -94,6 +99,8 @@ typedef struct {
   int32_t n_layers;          /* 0 = 6 */
   int32_t activation;        /* PAYNE_ACT_* ; must be LEAKY_RELU for 3/4 layers, SIGMOID for 6 */
   int32_t label_fp32_cast;   /* 1: labels pass through fp32 first (ANN.eval, predictspec.py:70); 0: fp64 (ystpred.py:47-50) */
+  int32_t n_groups;          /* multi-chunk emulator: number of chunk nets (0 or 1 = one monolithic net) */
+  int32_t group_size;        /* pixels per chunk net; the last one may be narrower (trainspec_multi.py:242-243) */
   int32_t reserved_;
 } PayneSpecNet;
 

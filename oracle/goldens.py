@@ -34,6 +34,11 @@ CASES = {
     # legacy leaky-ReLU emulators: SMLP = torch fp32, 4 layers; YST1 = numpy fp64, 3 layers
     'mini_smlp': (dict(kind='mini', nntype='SMLP'), 12, 12),
     'mini_yst': (dict(kind='mini', nntype='YST1', H=48), 12, 12),
+    # multi-chunk emulators (Payne/train/old/trainspec_multi.py): chunk widths that are / are not multiples
+    # of 32 pixels (one grouped launch / one launch per chunk for the output layers), and C4's chunked variant
+    'mini_multi': (dict(kind='mini', nntype='MultiNet', chunk=1024, H=64), 12, 12),
+    'mini_multi_odd': (dict(kind='mini', nntype='MultiNet', chunk=500, H=40, vmic=True), 8, 8),
+    'c4c': (dict(kind='c4c'), 6, 1),
     # C1: the reference's own demo (demo/runPayne.py:36-143): the spectrum and magnitudes of
     # demo/demodata.h5 (n_obs 25600, e = flux/25, 27 bands of which two have no high-Av coefficients)
     # against a random-init emulator of the demo's shape; the fixture carries the observation
@@ -67,7 +72,8 @@ def build(name, model_fn, data=None):
         return synth.config_c1(model_fn, obs_wave=wave, obs_flux=flux, obs_phot=phot, **kw)
     drop = kw.pop('drop', [])
     fixed = kw.pop('fixed', {})
-    base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3, 'c4': synth.config_c4}[kind]
+    base = {'mini': synth.config_mini, 'c2': synth.config_c2, 'c3': synth.config_c3, 'c4': synth.config_c4,
+            'c4c': synth.config_c4_chunked}[kind]
     if not drop and not fixed:
         return base(model_fn, **kw)
 

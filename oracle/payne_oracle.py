@@ -117,7 +117,43 @@ class LegacyNet:
         return np.array(out)      # [B, D_out] float64
 
 
+class MultiChunkNet:
+    """Multi-chunk emulator: one ``Net(D_in, H, P)`` per block of pixels
+    (``Payne/train/old/trainspec_multi.py:29-52``): ``encode`` = ``(x - xmin)/(xmax - xmin)`` in numpy on the
+    FloatTensor's values, no -0.5 (``:56-67``), then ``sigmoid(lin1), sigmoid(lin2), sigmoid(lin3), lin4``
+    in torch fp32; the chunks' outputs side by side make the spectrum."""
+
+    def __init__(self, spec, ideal=False):
+        self.spec, self.ideal = spec, ideal
+
+    def __call__(self, x):
+        sp = self.spec
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        dt = torch.float64 if self.ideal else torch.float32
+        x32 = torch.from_numpy(x).type(torch.FloatTensor)
+        enc = (x32.numpy() - sp.xmin) / (sp.xmax - sp.xmin)
+        h0 = torch.from_numpy(enc).type(torch.FloatTensor).to(dt)
+        out = []
+        lin = torch.nn.functional.linear
+        with torch.no_grad():
+            for g in range(sp.n_groups):
+                lo, hi = g * sp.chunk, min((g + 1) * sp.chunk, sp.D_out)
+                W = [torch.from_numpy(np.ascontiguousarray(sp.weights[k][g])).to(dt) for k in range(3)]
+                b = [torch.from_numpy(np.ascontiguousarray(sp.biases[k][g])).to(dt) for k in range(3)]
+                W4 = torch.from_numpy(np.ascontiguousarray(sp.weights[3][lo:hi])).to(dt)
+                b4 = torch.from_numpy(np.ascontiguousarray(sp.biases[3][lo:hi])).to(dt)
+                h = h0
+                for k in range(3):
+                    h = torch.sigmoid(lin(h, W[k], b[k]))
+                out.append(lin(h, W4, b4).numpy())
+        return np.concatenate(out, axis=1)
+
+
 def make_net(spec, ideal=False):
+    if spec.nntype == 'MultiNet':
+        return MultiChunkNet(spec, ideal=ideal)
     return TorchLinNet(spec, ideal=ideal) if spec.nntype == 'LinNet' else LegacyNet(spec, ideal=ideal)
 
 

@@ -77,12 +77,25 @@ def load():
         m.__path__ = [os.path.join(REF_ROOT, 'Payne', sub)]
         sys.modules['Payne.' + sub] = m
         setattr(pk, sub, m)
+    # train/old/trainspec_multi.py (the multi-chunk Net) sits one level deeper than when it was written:
+    # its `from ..utils.pullspectra import pullspectra` now resolves to Payne.train.utils, which does not
+    # exist; the trainer-only helper is never called on the prediction path
+    old = types.ModuleType('Payne.train.old')
+    old.__path__ = [os.path.join(REF_ROOT, 'Payne', 'train', 'old')]
+    sys.modules['Payne.train.old'] = old
+    tu = types.ModuleType('Payne.train.utils')
+    tu.__path__ = []
+    sys.modules['Payne.train.utils'] = tu
+    ps = types.ModuleType('Payne.train.utils.pullspectra')
+    ps.pullspectra = object
+    sys.modules['Payne.train.utils.pullspectra'] = ps
     ns = types.SimpleNamespace()
     for short, full in [('smoothing', 'Payne.utils.smoothing'), ('NNmodels', 'Payne.train.NNmodels'),
                         ('predictspec', 'Payne.predict.predictspec'), ('photANN', 'Payne.predict.photANN'),
                         ('highred', 'Payne.predict.highred'), ('predictsed', 'Payne.predict.predictsed'),
                         ('ystpred', 'Payne.predict.ystpred'), ('fitutils', 'Payne.fitting.fitutils'), ('genmod', 'Payne.fitting.genmod'),
-                        ('likelihood', 'Payne.fitting.likelihood'), ('prior', 'Payne.fitting.prior')]:
+                        ('likelihood', 'Payne.fitting.likelihood'), ('prior', 'Payne.fitting.prior'),
+                        ('trainspec_multi', 'Payne.train.old.trainspec_multi')]:
         setattr(ns, short, importlib.import_module(full))
     _mods = ns
     return ns
@@ -114,6 +127,39 @@ def build_likelihood(cfg):
         net.resolution = float(s.resolution)
         PP = R.ystpred.PayneSpecPredict.__new__(R.ystpred.PayneSpecPredict)
         PP.anns, PP.Canns, PP.NN, PP.NNtype = net, None, {}, 'YST1'
+        GM.PP = PP
+    elif like.spec_bool and getattr(s, 'nntype', 'LinNet') == 'MultiNet':
+        # The reference tree has no predictor for its own multi-chunk trainer output; the natural one is an
+        # ANN whose ``model`` runs every chunk's reference ``Net`` (trainspec_multi.py:29-67, built the way
+        # its readNN does, :717-737) and joins the outputs.  Everything downstream (ANN.eval, getspec,
+        # smoothspec, likelihood) is the unmodified reference.
+        class _Chunks(object):
+            def __init__(self, nets, D_in):
+                self.nets, self.D_in = nets, D_in
+
+            def __call__(self, xvar):
+                return torch.cat([n(xvar) for n in self.nets], dim=-1)
+        nets = []
+        H = s.weights[0].shape[1]
+        for g in range(s.n_groups):
+            lo, hi = g * s.chunk, min((g + 1) * s.chunk, s.D_out)
+            net = R.trainspec_multi.Net(s.D_in, H, hi - lo)
+            net.xmin, net.xmax = s.xmin, s.xmax
+            sd = {}
+            for k in range(3):
+                sd['lin%d.weight' % (k + 1)] = torch.from_numpy(s.weights[k][g].copy())
+                sd['lin%d.bias' % (k + 1)] = torch.from_numpy(s.biases[k][g].copy())
+            sd['lin4.weight'] = torch.from_numpy(s.weights[3][lo:hi].copy())
+            sd['lin4.bias'] = torch.from_numpy(s.biases[3][lo:hi].copy())
+            net.load_state_dict(sd)
+            net.eval()
+            nets.append(net)
+        ann = R.predictspec.ANN.__new__(R.predictspec.ANN)
+        ann.model, ann.wavelength = _Chunks(nets, s.D_in), s.wavelength.copy()
+        ann.resolution = np.array(s.resolution, dtype=float)
+        ann.xmin, ann.xmax, ann.inlabels, ann.NNtype = s.xmin, s.xmax, s.inlabels, 'MultiNet'
+        PP = R.predictspec.PayneSpecPredict.__new__(R.predictspec.PayneSpecPredict)
+        PP.anns, PP.Canns, PP.NN, PP.NNtype = ann, None, {}, 'MultiNet'
         GM.PP = PP
     elif like.spec_bool:
         nntype = getattr(s, 'nntype', 'LinNet')

@@ -78,3 +78,25 @@ def test_specnet_and_photnet_through_h5(tmp_path):
     annio.save_photnet(str(tmp_path / 'phot'), ph, fmt='h5')
     pb = annio.load_photnet(str(tmp_path / 'phot'), ph.bands, hiav=ph.hiav)
     assert np.array_equal(pb.w2, ph.w2) and np.array_equal(pb.xmax, ph.xmax)
+
+
+def test_multichunk_files_round_trip(tmp_path):
+    """The multi-chunk trainer's per-chunk files (train/old/trainspec_multi.py:300-313): written in its
+    layout, read back in any order, chunks re-assembled by wavelength."""
+    from thepayne_b200 import annio, synth
+    wave, rsig = synth.ann_wavegrid(5140.0, 5150.0, 50000.0)
+    net = synth.make_multinet(4, 24, wave, rsig, chunk=200, seed=3)
+    assert net.n_groups == (len(wave) + 199) // 200 and net.D_out == len(wave) and net.D_in == 4
+    paths = annio.save_multinet(str(tmp_path / 'ann'), net)
+    assert len(paths) == net.n_groups and all('_w' in p for p in paths)
+    d = h5lite.read(paths[1])
+    assert sorted(k.split('/')[-1] for k in d if 'model/' in k) == sorted(
+        ['lin%d.%s' % (k, w) for k in range(1, 5) for w in ('weight', 'bias')])
+    back = annio.load_multinet(list(reversed(paths)), net.xmin, net.xmax, net.resolution)
+    assert back.nntype == 'MultiNet' and back.chunk == 200 and back.encode_offset == 0.0
+    for a, b in zip(net.weights + net.biases, back.weights + back.biases):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(net.wavelength, back.wavelength)
+    assert back.digest() == net.digest()
+    back2 = annio.load_multinet(str(tmp_path / 'ann_w*.h5'), net.xmin, net.xmax, net.resolution)
+    assert back2.digest() == net.digest()

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpayne_b200.so')
 
-ABI_VERSION = 2          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
+ABI_VERSION = 3          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
 NPAR = 13
 MAX_POLY = 16
 PAR_INDEX = {
@@ -33,7 +33,7 @@ class PayneSpecNet(C.Structure):
                 ('D_out', C.c_int32), ('W', _f * 6), ('b', _f * 6), ('xmin', _d), ('xmax', _d),
                 ('wavelength', _d), ('resolution', C.c_double), ('encode_offset', C.c_double),
                 ('n_layers', C.c_int32), ('activation', C.c_int32), ('label_fp32_cast', C.c_int32),
-                ('reserved_', C.c_int32)]
+                ('n_groups', C.c_int32), ('group_size', C.c_int32), ('reserved_', C.c_int32)]
 
 
 class PaynePhotNet(C.Structure):

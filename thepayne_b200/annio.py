@@ -127,3 +127,68 @@ def load_photnet(dirpath, bands, hiav=None) -> PhotNet:
         hiav = np.array(highAv(bands).Avlist, dtype=np.float64)
     return PhotNet(list(bands), *[np.array(acc[k]) for k in ['w1', 'b1', 'w2', 'b2', 'w3', 'b3']],
                    xmin, xmax, np.asarray(hiav, dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-chunk emulator files (Payne/train/old/trainspec_multi.py).  The trainer writes one file per
+# chunk net, ``{prefix}_w{wavestart}_{waveend}.h5`` (:300-303), holding ``wavelength`` (the chunk's
+# pixels, :304-305) and the state dict under ``model_{wavestart}_{waveend}/model/lin{1..4}.{weight,bias}``
+# (gzip, :308-313).  Its reader takes the label limits from the caller (readNN(nnpath, wavestart,
+# wavestop, xmin, xmax), :717-737); so does this one, together with the emulator's sigma-resolution.
+def _chunk_path(prefix, w0, w1):
+    return '{0}_w{1}_{2}.h5'.format(prefix, w0, w1)
+
+
+def save_multinet(prefix, net: SpecNet):
+    """Write ``net`` (nntype 'MultiNet') as the trainer would: one .h5 per chunk; returns the paths."""
+    from . import h5lite
+    assert net.nntype == 'MultiNet'
+    paths = []
+    for g in range(net.n_groups):
+        lo, hi = g * net.chunk, min((g + 1) * net.chunk, net.D_out)
+        w = net.wavelength[lo:hi]
+        grp = 'model_{0}_{1}/model/'.format(w[0], w[-1])
+        d = {'wavelength': w}
+        for k in range(3):
+            d[grp + 'lin%d.weight' % (k + 1)] = net.weights[k][g]
+            d[grp + 'lin%d.bias' % (k + 1)] = net.biases[k][g]
+        d[grp + 'lin4.weight'] = net.weights[3][lo:hi]
+        d[grp + 'lin4.bias'] = net.biases[3][lo:hi]
+        path = _chunk_path(prefix, w[0], w[-1])
+        h5lite.write(path, d, gzip=('lin',))
+        paths.append(path)
+    return paths
+
+
+def load_multinet(paths, xmin, xmax, resolution, inlabels=None) -> SpecNet:
+    """Chunk files (any order; a glob pattern or a list of paths) -> one 'MultiNet' SpecNet with the
+    chunks sorted by wavelength.  Every chunk but the last must have the same number of pixels."""
+    import glob
+    if isinstance(paths, str):
+        paths = sorted(glob.glob(paths))
+    if not paths:
+        raise IOError('no multi-chunk emulator files found')
+    chunks = []
+    for p in paths:
+        d = _open(p)
+        wave = np.asarray(d['wavelength'], dtype=np.float64)
+        pre = [k[:-len('lin1.weight')] for k in d if k.endswith('model/lin1.weight')]
+        if len(pre) != 1:
+            raise IOError('%s: expected exactly one model_*/model group' % p)
+        g = pre[0]
+        W = [np.ascontiguousarray(np.asarray(d[g + 'lin%d.weight' % k], dtype=np.float32)) for k in range(1, 5)]
+        b = [np.ascontiguousarray(np.asarray(d[g + 'lin%d.bias' % k], dtype=np.float32)) for k in range(1, 5)]
+        if W[3].shape[0] != len(wave):
+            raise IOError('%s: lin4 has %d outputs for %d pixels' % (p, W[3].shape[0], len(wave)))
+        chunks.append((wave[0], wave, W, b))
+    chunks.sort(key=lambda c: c[0])
+    P = len(chunks[0][1])
+    if any(len(c[1]) != P for c in chunks[:-1]) or len(chunks[-1][1]) > P:
+        raise IOError('chunks must hold the same number of pixels (the last one may be narrower)')
+    xmin, xmax = np.asarray(xmin, dtype=np.float64), np.asarray(xmax, dtype=np.float64)
+    D_in = chunks[0][2][0].shape[1]
+    return SpecNet(weights=[np.stack([c[2][k] for c in chunks]) for k in range(3)] + [np.concatenate([c[2][3] for c in chunks], 0)],
+                   biases=[np.stack([c[3][k] for c in chunks]) for k in range(3)] + [np.concatenate([c[3][3] for c in chunks], 0)],
+                   xmin=xmin, xmax=xmax, wavelength=np.concatenate([c[1] for c in chunks]), resolution=float(resolution),
+                   inlabels=list(inlabels) if inlabels else ['teff', 'logg', 'feh', 'afe', 'vmic'][:D_in],
+                   encode_offset=0.0, nntype='MultiNet', chunk=int(P))

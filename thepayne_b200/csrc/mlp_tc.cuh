@@ -370,6 +370,13 @@ struct TcGemmArgs {
   long long ldc;
   float bias_shift;     // EPI 0: added to the bias (-1 makes the layer emit line depth f - 1)
   int M, N, K;
+  // Grouped launch (multi-chunk emulator, Payne/train/old/trainspec_multi.py:29-52): `groups` independent
+  // GEMMs of the same shape share one persistent grid; the tile index carries the group.  Group g reads
+  // activation rows [g a_grows, +M) of the planes, weight rows [g b_grows, +N) (bias / scale alike) and
+  // writes columns [g b_grows, +N) of the fp32 output (EPI 0) or plane rows offset by g out_gstride
+  // elements (EPI 1).  The last group may be narrower (n_last columns).  groups = 1: a plain GEMM.
+  int groups, n_last;
+  long long a_grows, b_grows, out_gstride;
 };
 
 // MC = 1: the CTAs of a 2-CTA cluster work on the SAME weight tile for two different row tiles;
@@ -399,7 +406,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   const int num_m_true = (G.M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
   // with MC the two CTAs of a cluster walk pair-tiles in lockstep: row tile 2*mp + crank
   const int num_m = MC ? (num_m_true + 1) / 2 : num_m_true;
-  const int num_tiles = num_m * num_n;
+  const int tiles_per_group = num_m * num_n;
+  const int num_tiles = tiles_per_group * G.groups;
   const int num_kb = (G.K + Cfg::kBK - 1) / Cfg::kBK;
   const int tile0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tstep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -429,7 +437,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
+        const int grp = tile / tiles_per_group, tig = tile - grp * tiles_per_group;
+        const int m0 = ((tig / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tig % num_n) * BN;
+        if (n0 >= (grp == G.groups - 1 ? G.n_last : G.N)) continue;       // narrower last group
+        const int arow = (int)(grp * G.a_grows) + m0, brow = (int)(grp * G.b_grows) + n0;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1);     // MC: both CTAs' MMAs have released this slot
           unsigned char* st = stages + s * Cfg::kStageBytes;
@@ -437,11 +448,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
           const int k0 = kb * Cfg::kBK;
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
-            ptx::tma_load_2d(&T.a[p], &full[s], st + p * Cfg::kABytes, k0, m0);
+            ptx::tma_load_2d(&T.a[p], &full[s], st + p * Cfg::kABytes, k0, arow);
             unsigned char* bdst = st + NP * Cfg::kABytes + p * Cfg::kBBytes;
             if (MC) ptx::tma_load_2d_mc(&T.b[p], &full[s], bdst + crank * (Cfg::kBBytes / 2), k0,
-                                        n0 + (int)crank * (BN / 2), (uint16_t)3);
-            else ptx::tma_load_2d(&T.b[p], &full[s], bdst, k0, n0);
+                                        brow + (int)crank * (BN / 2), (uint16_t)3);
+            else ptx::tma_load_2d(&T.b[p], &full[s], bdst, k0, brow);
           }
           if (++s == NS) { s = 0; ph ^= 1; }
         }
@@ -454,6 +465,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        {
+          const int grp = tile / tiles_per_group, tig = tile - grp * tiles_per_group;
+          if ((tig % num_n) * BN >= (grp == G.groups - 1 ? G.n_last : G.N)) continue;
+        }
         ptx::mbar_wait(&tempty[acc], aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
@@ -501,7 +516,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
     float* pt = patch + q * (EPI == 0 ? 1024 : 32 * 33);     // EPI 0: 4 KB swizzled staging block
     int acc = 0; uint32_t aph = 0;
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
-      const int m0 = ((tile / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tile % num_n) * BN;
+      const int grp = tile / tiles_per_group, tig = tile - grp * tiles_per_group;
+      const int m0 = ((tig / num_n) * (MC ? 2 : 1) + (int)crank) * kBM, n0 = (tig % num_n) * BN;
+      const int Ng = grp == G.groups - 1 ? G.n_last : G.N;         // this group's output width
+      if (n0 >= Ng) continue;
+      const int gcol = (int)(grp * G.b_grows);                     // bias / scale / output-column offset
+      const long long gout = grp * G.out_gstride;                  // EPI 1: plane offset of the group
       constexpr bool kRegEpi = (EPI == 1 && MODE == kModeX3);   // hidden layer, rows stay in registers
       if constexpr (EPI == 0 || kRegEpi) {
         // bias (+shift) and scale of this tile's columns -> shared memory, before the accumulator
@@ -510,8 +530,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
         ptx::epi_bar_sync_n<kEpiThreads>();        // previous tile's readers are done
         for (int cix = threadIdx.x - 128; cix < BN; cix += kEpiThreads) {
           const int gc = n0 + cix;
-          sbias[cix] = (gc < G.N ? __ldg(G.bias + gc) : 0.f) + G.bias_shift;
-          sscale[cix] = (MODE == kModeX3 && gc < G.N) ? __ldg(G.wscale + gc) : 1.f;
+          sbias[cix] = (gc < Ng ? __ldg(G.bias + gcol + gc) : 0.f) + G.bias_shift;
+          sscale[cix] = (MODE == kModeX3 && gc < Ng) ? __ldg(G.wscale + gcol + gc) : 1.f;
         }
         ptx::epi_bar_sync_n<kEpiThreads>();
       }
@@ -523,12 +543,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           const int col0 = n0 + ch * 32;
-          if (col0 >= G.N) break;
+          if (col0 >= Ng) break;
           uint32_t v[32], c[32];
           ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
           if constexpr (MODE == kModeX3) ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
           ptx::tmem_ld_wait();
-          epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
+          epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, gcol + col0, row_base, lane);
         }
       } else if constexpr (kRegEpi) {
         // Hidden layer: thread = row.  Its 32 accumulator columns never leave registers:
@@ -538,14 +558,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
         const bool rowok = grow < G.M;
         constexpr int NG = TcThreads<MODE, EPI>::kEpiWarps / 4, CW = BN / NG;   // column groups, columns each
         static_assert(CW == 16, "hidden-layer epilogue: 16 columns per warp group");
-        const int grp = (warp - 4) >> 2;
-        const int cbase = grp * CW, col0 = n0 + cbase;
-        if (col0 < G.N) {
+        const int wgrp = (warp - 4) >> 2;
+        const int cbase = wgrp * CW, col0 = n0 + cbase;
+        if (col0 < Ng) {
           uint32_t v[CW], c[CW];
           ptx::tmem_ld16_nowait(t_main + (uint32_t)cbase, v);
           ptx::tmem_ld16_nowait(t_main + (uint32_t)(BN + cbase), c);
           ptx::tmem_ld_wait();
-          const long long o = (long long)grow * G.ldc + col0;
+          const long long o = gout + (long long)grow * G.ldc + col0;
           const float4* b4 = reinterpret_cast<const float4*>(sbias + cbase);
           const float4* s4 = reinterpret_cast<const float4*>(sscale + cbase);
 #pragma unroll
@@ -564,14 +584,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
             }
             if (rowok) {
               const int gc = col0 + 8 * g8;
-              if (gc + 8 <= G.N) {
+              if (gc + 8 <= Ng) {
                 *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out0 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q1);
                 *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out1 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q2);
                 *reinterpret_cast<uint4*>((__nv_bfloat16*)G.out2 + o + 8 * g8) = *reinterpret_cast<const uint4*>(q3);
               } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                  if (gc + e < G.N) {
+                  if (gc + e < Ng) {
                     ((__nv_bfloat16*)G.out0)[o + 8 * g8 + e] = q1[e];
                     ((__nv_bfloat16*)G.out1)[o + 8 * g8 + e] = q2[e];
                     ((__nv_bfloat16*)G.out2)[o + 8 * g8 + e] = q3[e];
@@ -584,7 +604,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col0 = n0 + ch * 32;
-        if (col0 >= G.N) break;
+        if (col0 >= Ng) break;
         uint32_t v[32];
         ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
         if constexpr (MODE == kModeX3) {
@@ -599,18 +619,18 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
           for (int j = 0; j < 32; ++j) pt[lane * 33 + j] = __uint_as_float(v[j]);
         }
         __syncwarp();
-        const int gcol = col0 + lane;
-        const bool colok = gcol < G.N;
-        float bv = colok ? __ldg(G.bias + gcol) : 0.f;
+        const int lcol = col0 + lane;
+        const bool colok = lcol < Ng;
+        float bv = colok ? __ldg(G.bias + gcol + lcol) : 0.f;
         if (EPI == 0) bv += G.bias_shift;
-        const float sc = (MODE == kModeX3 && colok) ? __ldg(G.wscale + gcol) : 1.f;
+        const float sc = (MODE == kModeX3 && colok) ? __ldg(G.wscale + gcol + lcol) : 1.f;
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
           const int grow = row_base + r;
           if (grow >= G.M) break;
           float val = fmaf(pt[r * 33 + lane], sc, bv);
           if (colok) {
-            const long long o = (long long)grow * G.ldc + gcol;
+            const long long o = (EPI == 0 ? (long long)gcol : gout) + (long long)grow * G.ldc + lcol;
             if (EPI == 0) {
               ((float*)G.out0)[o] = val;
             } else {
@@ -845,9 +865,15 @@ __global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __
 __global__ void __launch_bounds__(256)
 encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __restrict__ x, long long ld,
                         const float* __restrict__ W1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ p1,
-                        __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldp, int B) {
+                        __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldp, int B,
+                        long long plane_gstride) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // multi-chunk emulator: blockIdx.y = chunk net; its first layer follows the previous one in W1 / b1 and
+  // its operand planes start plane_gstride elements further on (gridDim.y = 1 otherwise)
+  W1 += (long long)blockIdx.y * E.H1 * E.D_in;
+  b1 += (long long)blockIdx.y * E.H1;
+  p1 += blockIdx.y * plane_gstride; p2 += blockIdx.y * plane_gstride; p3 += blockIdx.y * plane_gstride;
   // lets the first tensor-core layer (launched with programmatic stream serialization) get resident and
   // run its prologue now; it still waits for this grid to finish before touching the planes
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1013,14 +1039,24 @@ inline bool tc_pdl_enabled() {
   return v != 0;
 }
 
+// Groups of a grouped launch (see TcGemmArgs).  n = output width of every group but the last.
+struct TcGroups {
+  int groups = 1, n = 0, n_last = 0;
+  long long a_grows = 0, out_gstride = 0;
+};
+
 template <int BN, int MODE, int EPI, int MC>
 inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                           void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
-                          TcMapCache* cache = nullptr, long long map_rows = 0) {
+                          TcMapCache* cache = nullptr, long long map_rows = 0, const TcGroups* grp = nullptr,
+                          int out_cols = 0) {
   using Cfg = TcCfg<BN, MODE>;
   static_assert(Cfg::kStages >= 2, "ring too shallow");
   constexpr int kVariant = BN * 1000 + MODE * 100 + EPI * 10 + MC;
-  const long long mrows = (cache && map_rows >= M) ? map_rows : M;
+  const bool grouped = grp && grp->groups > 1;
+  if (grouped && MC) return PAYNE_E_UNSUPPORTED;
+  // grouped: the maps span every group's rows of the planes (a_grows rows each)
+  const long long mrows = grouped ? grp->groups * grp->a_grows : ((cache && map_rows >= M) ? map_rows : M);
   TcMaps local;
   TcMaps& T = cache ? cache->maps : local;
   const bool hit = cache && cache->variant == kVariant && cache->a0 == A.plane[0] && cache->out == out0 &&
@@ -1033,8 +1069,10 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
       if (make_tmap(&T.b[p], wp, W.N, K, W.Kp, MC ? BN / 2 : BN, Cfg::kElemBytes)) return PAYNE_E_CUDA;
     }
     for (int p = Cfg::kPlanes; p < 3; ++p) { T.a[p] = T.a[0]; T.b[p] = T.b[0]; }
-    if (EPI == 0) { if (int rc = make_tmap_out(&T.c, out0, mrows, W.N, ldc)) return rc; }
-    else T.c = T.a[0];
+    if (EPI == 0) {
+      const long long orows = grouped ? ((cache && map_rows >= M) ? map_rows : M) : mrows;
+      if (int rc = make_tmap_out(&T.c, out0, orows, out_cols > 0 ? out_cols : W.N, ldc)) return rc;
+    } else T.c = T.a[0];
     if (cache) {
       cache->a0 = A.plane[0]; cache->out = out0; cache->rows = mrows; cache->lda = A.ld; cache->ldc = ldc;
       cache->variant = kVariant;
@@ -1049,8 +1087,12 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
                              Cfg::kSmem) != cudaSuccess) return PAYNE_E_CUDA;
     if (dev < 64) attr_set |= 1ull << dev;
   }
-  TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K};
-  const int num_m = (M + kBM - 1) / kBM, num_n = (W.N + BN - 1) / BN;
+  TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
+  if (grouped) {
+    G.N = grp->n; G.groups = grp->groups; G.n_last = grp->n_last; G.a_grows = grp->a_grows; G.b_grows = grp->n;
+    G.out_gstride = grp->out_gstride;
+  }
+  const int num_m = (M + kBM - 1) / kBM, num_n = (G.N + BN - 1) / BN;
   if (MC) {
     const int pair_tiles = ((num_m + 1) / 2) * num_n;
     int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
@@ -1062,7 +1104,7 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
     cfg.attrs = at; cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, EPI, MC>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
   } else {
-    const int tiles = num_m * num_n;
+    const int tiles = num_m * num_n * G.groups;
     const int grid = tiles < sm_count ? tiles : sm_count;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TcThreads<MODE, EPI>::value); cfg.dynamicSmemBytes = Cfg::kSmem;
@@ -1104,7 +1146,7 @@ inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float
       return PAYNE_E_CUDA;
     if (dev < 64) attr_set |= 1ull << dev;
   }
-  TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K};
+  TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
   const int pair_tiles = ((M + 255) / 256) * ((W.N + BN - 1) / BN);
   const int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
   cudaLaunchConfig_t cfg{};
@@ -1120,7 +1162,11 @@ inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float
 template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                      void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
-                     TcMapCache* cache = nullptr, long long map_rows = 0) {
+                     TcMapCache* cache = nullptr, long long map_rows = 0, const TcGroups* grp = nullptr,
+                     int out_cols = 0) {
+  if (grp && grp->groups > 1)
+    return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
+                                            map_rows, grp, out_cols);
   if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 1)
     return tc_launch_2sm<128>(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st, map_rows);
   if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 2)
@@ -1163,6 +1209,73 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
                                sm_count, st, caches ? caches + 5 : nullptr, out_rows >= cur->rows ? cur->rows : 0);
   ++*launches;
   return rc;
+}
+
+// Multi-chunk emulator (Payne/train/old/trainspec_multi.py:29-52): G nets Net(D_in, H, P), sigmoid, 4 layers.
+// lin1 was written by the caller as sliced planes [G][rows, H]; here lin2, lin3 (grouped hidden GEMMs) and
+// lin4, whose G output blocks of P columns make up the contiguous flux row.  One launch per layer when
+// every chunk but the last is a multiple of 32 pixels wide (TMA-store boxes are 32 columns; a partial
+// box of chunk g would overwrite columns of chunk g+1), otherwise one launch per chunk for lin4.
+template <int MODE>
+inline int tc_run_multinet_mode(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,
+                                TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out,
+                                long long ldo, float bias_shift, int sm_count, cudaStream_t st, long long* launches,
+                                long long out_rows) {
+  TcGroups gh;
+  gh.groups = groups; gh.n = H; gh.n_last = H; gh.a_grows = rows_per_group; gh.out_gstride = rows_per_group * actA->ld;
+  TcActs* cur = actA; TcActs* nxt = actB;
+  int rc = PAYNE_OK;
+  for (int k = 1; k <= 2 && !rc; ++k) {
+    rc = tc_launch<64, MODE, 1>(*cur, H, tcw[k], bias[k], nxt->plane[0], nxt->plane[1], nxt->plane[2], nxt->ld, 0.f,
+                                nb, sm_count, st, nullptr, 0, &gh);
+    ++*launches;
+    TcActs* t = cur; cur = nxt; nxt = t;
+  }
+  if (rc) return rc;
+  const int n_last = D_out - (groups - 1) * chunk;
+  if (chunk % 32 == 0 || groups == 1) {
+    TcGroups g4;
+    g4.groups = groups; g4.n = chunk; g4.n_last = n_last; g4.a_grows = rows_per_group; g4.out_gstride = 0;
+    rc = tc_launch<PAYNE_LIN6_BN, MODE, 0>(*cur, H, tcw[3], bias[3], out, nullptr, nullptr, ldo, bias_shift, nb, sm_count,
+                                           st, nullptr, out_rows, &g4, D_out);
+    ++*launches;
+    return rc;
+  }
+  for (int g = 0; g < groups && !rc; ++g) {              // general chunk widths: one GEMM per chunk
+    TcActs a = *cur;
+    const long long off = (long long)g * rows_per_group * cur->ld;
+    for (int p = 0; p < 3; ++p) a.plane[p] = (char*)cur->plane[p] + off * (MODE == kModeX3 ? 2 : 4);
+    a.rows = rows_per_group;
+    TcWeights w = tcw[3];
+    const int ng = g == groups - 1 ? n_last : chunk;
+    const long long woff = (long long)g * chunk * w.Kp;
+    for (int p = 0; p < 3; ++p) {
+      if (w.plane[p]) w.plane[p] = (char*)w.plane[p] + woff * 4;
+      if (w.xplane[p]) w.xplane[p] = (char*)w.xplane[p] + woff * 2;
+    }
+    w.scale = tcw[3].scale + (long long)g * chunk;
+    w.N = ng;
+    // the output map of this chunk covers exactly its ng columns: TMA clips the partial box.  The base
+    // must be 16-byte aligned: chunk widths that are not multiples of 4 go through the SIMT layers.
+    rc = tc_launch<PAYNE_LIN6_BN, MODE, 0>(a, H, w, bias[3] + (long long)g * chunk, out + (long long)g * chunk, nullptr,
+                                           nullptr, ldo, bias_shift, nb, sm_count, st, nullptr, out_rows);
+    ++*launches;
+  }
+  return rc;
+}
+
+inline int tc_run_multinet(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,
+                           TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out, long long ldo,
+                           float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                           long long out_rows) {
+  if (prec == PAYNE_PREC_PARITY && H > kX3MaxK) return PAYNE_E_UNSUPPORTED;
+  switch (prec) {
+    case PAYNE_PREC_PARITY:
+      return tc_run_multinet_mode<kModeX3>(tcw, bias, H, D_out, groups, chunk, actA, actB, rows_per_group, nb, out,
+                                           ldo, bias_shift, sm_count, st, launches, out_rows);
+    default:
+      return PAYNE_E_UNSUPPORTED;
+  }
 }
 
 // lin2..lin6 from the fp32 output of lin1 (h1, pitch = dims_out[0]).  bias_shift is added to the

@@ -121,6 +121,10 @@ struct PayneCtx {
   cudaStream_t stream = nullptr;   // used by the *_host entry
   int n_layers = 6;
   bool legacy = false;             // leaky-ReLU stack (SMLP / YST1): CUDA-core fp32 layers only
+  // multi-chunk emulator (trainspec_multi.py:29-52): n_groups sigmoid nets of 4 layers, `chunk` pixels each
+  bool multinet = false;
+  int n_groups = 1, chunk = 0;
+  long long rows_per_group = 0;    // rows of one group's block in the activation planes (workspace)
   payne::TcMapCache mapc[6];       // tensor maps per layer, valid while the workspace stays put
   cudaStream_t side = nullptr;     // per-point tail setup runs here, beside the emulator GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -206,11 +210,19 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   if (s->D_in < 1 || s->D_in > 8) return fail(PAYNE_E_INVALID, "D_in must be in [1,8]");
   if (s->D_out < 32) return fail(PAYNE_E_INVALID, "D_out must be >= 32");
   const int nl = s->n_layers == 0 ? 6 : s->n_layers;
-  if (nl != 6 && nl != 4 && nl != 3) return fail(PAYNE_E_INVALID, "n_layers must be 6 (LinNet), 4 (SMLP) or 3 (YST1)");
-  if ((nl == 6) != (s->activation == PAYNE_ACT_SIGMOID))
-    return fail(PAYNE_E_UNSUPPORTED, "supported emulators: 6 sigmoid layers, or 3/4 leaky-ReLU layers");
+  if (nl != 6 && nl != 4 && nl != 3) return fail(PAYNE_E_INVALID, "n_layers must be 6 (LinNet), 4 (SMLP / multi-chunk) or 3 (YST1)");
+  c->multinet = (nl == 4 && s->activation == PAYNE_ACT_SIGMOID && s->n_groups >= 1);
+  if (!c->multinet && (nl == 6) != (s->activation == PAYNE_ACT_SIGMOID))
+    return fail(PAYNE_E_UNSUPPORTED, "supported emulators: 6 sigmoid layers, 4 sigmoid layers in chunks, or 3/4 leaky-ReLU layers");
   c->n_layers = nl;
-  c->legacy = (nl != 6);
+  c->legacy = (nl != 6) && !c->multinet;
+  if (c->multinet) {
+    c->n_groups = s->n_groups; c->chunk = s->group_size;
+    if (c->chunk < 32 || (long long)(c->n_groups - 1) * c->chunk >= s->D_out || (long long)c->n_groups * c->chunk < s->D_out)
+      return fail(PAYNE_E_INVALID, "multi-chunk emulator: n_groups chunks of group_size pixels must tile D_out (last one may be narrower)");
+    if (s->H2 != s->H1 || s->H3 != s->H1) return fail(PAYNE_E_INVALID, "multi-chunk emulator: H2 and H3 must equal H1");
+    if (c->n_groups > 64) return fail(PAYNE_E_UNSUPPORTED, "at most 64 chunk nets");
+  }
   int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
   int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
   if (nl == 4) {                                   // NNmodels.py:99-107
@@ -219,6 +231,12 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   } else if (nl == 3) {                            // ystpred.py:25-30
     const int a[3] = {s->D_in, s->H1, s->H2}, b[3] = {s->H1, s->H2, s->D_out};
     for (int k = 0; k < 3; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  }
+  if (c->multinet) {
+    // stacked over the chunks: [G*H, D_in], [G*H, H], [G*H, H], [D_out, H]
+    const int G = c->n_groups, H = s->H1;
+    const int a[4] = {s->D_in, H, H, H}, b[4] = {G * H, G * H, G * H, s->D_out};
+    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
   }
   for (int k = 0; k < nl; ++k) {
     c->dims_in[k] = din[k]; c->dims_out[k] = dout[k];
@@ -229,7 +247,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   }
   EncodeParams& E = c->enc;
   E.D_in = s->D_in; E.H1 = s->H1; E.offset = s->encode_offset;
-  E.cast32 = (nl == 6) ? 1 : (s->label_fp32_cast != 0);
+  E.cast32 = (nl == 6 || c->multinet) ? 1 : (s->label_fp32_cast != 0);
   E.act = c->legacy ? kActLeaky : kActSigmoid;
   const int label_par[5] = {PAYNE_P_TEFF, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VMIC};
   for (int i = 0; i < 8; ++i) {
@@ -480,10 +498,28 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   // Parity mode's "the tensor core never rounds the leading product sum" holds for contractions up to
   // 512 wide (mlp_tc.cuh header); wider hidden layers must use the CUDA-core fp32 mode.
   if (!c->legacy && c->lay.precision == PAYNE_PREC_PARITY)
-    for (int k = 1; k < 6; ++k)
+    for (int k = 1; k < (c->multinet ? 4 : 6); ++k)
       if (din[k] > payne::kX3MaxK)
         return fail(PAYNE_E_UNSUPPORTED, "parity precision supports hidden widths up to 512 (layer " + std::to_string(k + 1) +
                     " contracts over " + std::to_string(din[k]) + "); use precision 'simt'");
+  if (c->multinet) {
+    // chunk widths that are not multiples of 4 cannot be TMA-stored (16-byte bases): CUDA-core layers
+    if (c->chunk % 4 != 0 && c->lay.precision != PAYNE_PREC_SIMT_FP32)
+      return fail(PAYNE_E_UNSUPPORTED, "multi-chunk emulator: group_size must be a multiple of 4 for the tensor-core modes (use precision 'simt')");
+    if (c->lay.precision != PAYNE_PREC_SIMT_FP32 && c->lay.precision != PAYNE_PREC_PARITY)
+      return fail(PAYNE_E_UNSUPPORTED, "multi-chunk emulator: precision must be 'parity' or 'simt'");
+    const int G = c->n_groups, H = s->H1;
+    for (int k = 1; k <= 2; ++k) {
+      rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], G * H, H, &c->owned);
+      if (rc) return fail(rc, "tc_prepare_weights failed");
+    }
+    // output layers padded to G * chunk rows so that every group's weight block has the same height
+    std::vector<float> w4((size_t)G * c->chunk * H, 0.f);
+    std::memcpy(w4.data(), s->W[3], (size_t)s->D_out * H * sizeof(float));
+    rc = payne::tc_prepare_weights(&c->tcw[3], w4.data(), G * c->chunk, H, &c->owned);
+    if (rc) return fail(rc, "tc_prepare_weights failed");
+    return PAYNE_OK;
+  }
   // tensor-core operand copies of the weights (sigmoid LinNet only)
   for (int k = 1; k < 6 && !c->legacy; ++k) {
     rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
@@ -538,14 +574,16 @@ int ensure_workspace(PayneCtx* c, long long B) {
   const long long rows = (need + 127) / 128 * 128;
   if (c->has_spec) {
     const long long hmax = (std::max({c->H[0], c->H[1], c->H[2]}) + 7) / 8 * 8;
+    const long long arows = rows * c->n_groups;          // multi-chunk: one block of `rows` rows per chunk net
+    c->rows_per_group = rows;
     CU_TRY(cudaMalloc((void**)&c->flux, (size_t)rows * c->ldf * sizeof(float)));
     CU_TRY(cudaMemset(c->flux, 0, (size_t)rows * c->ldf * sizeof(float)));   // the row padding stays zero
-    CU_TRY(cudaMalloc((void**)&c->hA, (size_t)rows * hmax * sizeof(float)));
-    CU_TRY(cudaMalloc((void**)&c->hB, (size_t)rows * hmax * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&c->hA, (size_t)arows * hmax * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&c->hB, (size_t)arows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
     CU_TRY(cudaMemset(c->fast.points, 0, (size_t)rows * sizeof(payne::FastPoint)));   // struct padding is copied too
-    int rc = payne::tc_alloc_acts(&c->actA, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
-    rc = payne::tc_alloc_acts(&c->actB, rows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+    int rc = payne::tc_alloc_acts(&c->actA, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+    rc = payne::tc_alloc_acts(&c->actB, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
   }
   CU_TRY(cudaMalloc((void**)&c->chi2_sed, (size_t)rows * sizeof(double)));
   // the zero-fills above went to the NULL stream; callers may launch on non-blocking streams that do
@@ -562,12 +600,50 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
             float* out, long long ldo, bool want_depth, int* is_depth, cudaStream_t st) {
   using namespace payne;
   const int prec = c->lay.precision;
+  if (c->multinet) {
+    // ---- multi-chunk emulator: G independent 4-layer sigmoid nets, outputs side by side in the flux row
+    const int G = c->n_groups, H = c->H[0], P = c->chunk;
+    const long long rpg = c->rows_per_group;
+    *is_depth = want_depth ? 1 : 0;
+    if (prec == PAYNE_PREC_SIMT_FP32) {
+      const long long hld = (std::max({c->H[0], c->H[1], c->H[2]}) + 7) / 8 * 8;
+      for (int g = 0; g < G; ++g) {
+        float* a = c->hA + (size_t)g * rpg * hld; float* b = c->hB + (size_t)g * rpg * hld;
+        const long long tot = (long long)nb * H;
+        encode_layer1_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+            E, x, ld, c->W[0] + (size_t)g * H * c->D_in, c->b[0] + (size_t)g * H, a, hld, nb);
+        dim3 gh((H + 127) / 128, (nb + 127) / 128);
+        sgemm_bias_act_kernel<kActSigmoid><<<gh, 256, 0, st>>>(a, hld, c->W[1] + (size_t)g * H * H, c->b[1] + (size_t)g * H,
+                                                                b, hld, nb, H, H, 0.f);
+        sgemm_bias_act_kernel<kActSigmoid><<<gh, 256, 0, st>>>(b, hld, c->W[2] + (size_t)g * H * H, c->b[2] + (size_t)g * H,
+                                                                a, hld, nb, H, H, 0.f);
+        const int ng = g == G - 1 ? c->D_out - (G - 1) * P : P;
+        dim3 g4((ng + 127) / 128, (nb + 127) / 128);
+        sgemm_bias_act_kernel<kActNone><<<g4, 256, 0, st>>>(a, hld, c->W[3] + (size_t)g * P * H, c->b[3] + (size_t)g * P,
+                                                             out + (size_t)g * P, ldo, nb, ng, H, want_depth ? -1.f : 0.f);
+        c->launches += 4;
+      }
+      CU_TRY(cudaGetLastError());
+      return PAYNE_OK;
+    }
+    dim3 ge((unsigned)((nb + 7) / 8), (unsigned)G);
+    encode_layer1_x3_kernel<<<ge, 256, 0, st>>>(
+        E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
+        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb, rpg * c->actA.ld);
+    c->launches++;
+    int rc = tc_run_multinet(c->tcw, c->b, H, c->D_out, G, P, &c->actA, &c->actB, rpg, nb, out, ldo,
+                             want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches,
+                             out == c->flux ? rpg : 0);
+    if (rc) return fail(rc, "tensor-core multi-chunk path failed");
+    CU_TRY(cudaGetLastError());
+    return PAYNE_OK;
+  }
   const bool simt = c->legacy || prec == PAYNE_PREC_SIMT_FP32;
   const bool fused_split = !simt && (prec == PAYNE_PREC_PARITY);   // encode + lin1 + slicing in one kernel
   if (fused_split) {
     encode_layer1_x3_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(
         E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
-        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb);
+        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb, 0);
   } else {
     const long long tot = (long long)nb * c->H[0];
     encode_layer1_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, x, ld, c->W[0], c->b[0], c->hA,
@@ -854,8 +930,10 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   std::string k(key);
   if (k == "precision") {
     if (value < 0 || value > 4 || value == PAYNE_PREC_BF16) return fail(PAYNE_E_INVALID, "unknown precision");
+    if (c->multinet && value != PAYNE_PREC_PARITY && value != PAYNE_PREC_SIMT_FP32)
+      return fail(PAYNE_E_UNSUPPORTED, "multi-chunk emulator: precision must be 'parity' or 'simt'");
     if (value == PAYNE_PREC_PARITY && c->has_spec && !c->legacy)
-      for (int k = 1; k < 6; ++k)
+      for (int k = 1; k < (c->multinet ? 4 : 6); ++k)
         if (c->dims_in[k] > payne::kX3MaxK)
           return fail(PAYNE_E_UNSUPPORTED, "parity precision supports hidden widths up to 512");
     c->lay.precision = (int)value;

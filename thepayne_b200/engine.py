@@ -73,17 +73,20 @@ class Engine:
             keep += W + b
             nl = len(W)
             nntype = getattr(spec, 'nntype', 'LinNet')
-            if (nl, nntype) not in [(6, 'LinNet'), (4, 'SMLP'), (3, 'YST1')]:
+            if (nl, nntype) not in [(6, 'LinNet'), (4, 'SMLP'), (3, 'YST1'), (4, 'MultiNet')]:
                 raise ValueError('unsupported emulator: %d layers of type %s' % (nl, nntype))
-            sp.D_in, sp.H1, sp.D_out = W[0].shape[1], W[0].shape[0], W[-1].shape[0]
-            if nl == 6:          # NNmodels.py:147-152
+            sp.D_in, sp.H1, sp.D_out = W[0].shape[-1], W[0].shape[-2], W[-1].shape[0]
+            if nntype == 'MultiNet':   # trainspec_multi.py:29-36, chunk nets stacked along axis 0
+                sp.H2 = sp.H3 = sp.H1
+                sp.n_groups, sp.group_size = int(W[0].shape[0]), int(spec.chunk)
+            elif nl == 6:        # NNmodels.py:147-152
                 sp.H2, sp.H3 = W[3].shape[0], W[4].shape[0]
             elif nl == 4:        # NNmodels.py:99-107
                 sp.H2, sp.H3 = W[1].shape[0], W[2].shape[0]
             else:                # ystpred.py:25-30
                 sp.H2, sp.H3 = W[1].shape[0], 0
             sp.n_layers = nl
-            sp.activation = 0 if nntype == 'LinNet' else 1
+            sp.activation = 0 if nntype in ('LinNet', 'MultiNet') else 1
             sp.label_fp32_cast = 0 if nntype == 'YST1' else 1      # ystpred.py:47-50 stays in float64
             for k in range(nl):
                 sp.W[k], sp.b[k] = _pf(W[k]), _pf(b[k])

@@ -36,7 +36,7 @@ from scipy.special import logsumexp
 
 class BatchedNestedSampler(object):
     def __init__(self, lnprob_batch, prior_transform_batch, ndim, nlive=125, walks=25, queue_size=None,
-                 facc=0.5, reflective=(), seed=None, max_extra_walks=20):
+                 facc=0.5, reflective=(), seed=None, max_extra_walks=0):
         """``lnprob_batch(theta[B, ndim]) -> lnP[B]`` (``BatchedLnProb.batch``) and
         ``prior_transform_batch(U[B, ndim]) -> theta[B, ndim]`` (``prior.priortrans_batch``)."""
         self.lnprob_batch = lnprob_batch
@@ -134,7 +134,9 @@ class BatchedNestedSampler(object):
                 nrej[ev[~ok]] += 1
             step += 1
             if step >= self.walks:
-                # like dynesty, a walk does not end before it has moved at least once
+                # dynesty lets a walk that has not moved yet go on until it does; in lock-step those
+                # stragglers would arrive in calls of a handful of points, so by default
+                # (max_extra_walks = 0) a walker that never moved simply yields no proposal
                 active = active[nacc[active] == 0]
                 if step >= self.walks * (1 + self.max_extra):
                     break

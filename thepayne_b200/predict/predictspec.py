@@ -31,8 +31,8 @@ class ANN(object):
         self.verbose = kwargs.get('verbose', False)
         self.nnpath = nnpath
         self.NNtype = kwargs.get('NNtype', 'LinNet')
-        if self.NNtype not in ('LinNet', 'SMLP', 'YST1'):
-            raise NotImplementedError('NNtype=%r is not accelerated (LinNet, SMLP and YST1 are)' % self.NNtype)
+        if self.NNtype not in ('LinNet', 'SMLP', 'YST1', 'MultiNet'):
+            raise NotImplementedError('NNtype=%r is not accelerated (LinNet, SMLP, YST1 and MultiNet are)' % self.NNtype)
         self.model = _as_specnet(nnpath, self.NNtype)
         if self.model.nntype != self.NNtype:
             raise ValueError('NNtype=%r but the network container holds a %s' % (self.NNtype, self.model.nntype))

@@ -35,12 +35,20 @@ class SpecNet:
     inlabels: list = field(default_factory=lambda: ['teff', 'logg', 'feh', 'afe'])
     encode_offset: float = 0.5   # LinNet subtracts 0.5 (NNmodels.py:166)
     # 'LinNet' (6 x Linear, sigmoid; NNmodels.py:140-162), 'SMLP' (4 x Linear, LeakyReLU, torch fp32;
-    # NNmodels.py:92-115) or 'YST1' (3 layers, leaky ReLU, numpy fp64; predict/ystpred.py:18-58)
+    # NNmodels.py:92-115), 'YST1' (3 layers, leaky ReLU, numpy fp64; predict/ystpred.py:18-58) or
+    # 'MultiNet' (G chunk nets Net(D_in,H,P) of 4 sigmoid/linear layers, train/old/trainspec_multi.py:29-52:
+    # weights = [W1 [G,H,D_in], W2 [G,H,H], W3 [G,H,H], W4 [D_out,H]] with the chunks' output layers one
+    # after another, biases alike, ``chunk`` = pixels per net, encode_offset 0)
     nntype: str = 'LinNet'
+    chunk: int = 0
+
+    @property
+    def n_groups(self):
+        return int(self.weights[0].shape[0]) if self.nntype == 'MultiNet' else 1
 
     @property
     def D_in(self):
-        return int(self.weights[0].shape[1])
+        return int(self.weights[0].shape[-1])
 
     @property
     def D_out(self):
@@ -122,6 +130,33 @@ def make_specnet(D_in, H, wave, resolution, seed=0, out_scale=0.3, out_bias=1.0,
         resolution=float(resolution), inlabels=labels, nntype=nntype)
 
 
+def make_multinet(D_in, H, wave, resolution, chunk, seed=0, out_scale=0.3, out_bias=1.0):
+    """Random-init multi-chunk emulator: one ``Net(D_in, H, P)`` (lin1..lin4 created in that order,
+    trainspec_multi.py:29-36) per ``chunk`` pixels, last one narrower; output layers scaled like
+    make_specnet's so the flux looks like a normalised spectrum."""
+    D_out = len(wave)
+    G = (D_out + chunk - 1) // chunk
+    torch.manual_seed(seed)
+    W1, W2, W3, W4, b1, b2, b3, b4 = [], [], [], [], [], [], [], []
+    for g in range(G):
+        P = min(chunk, D_out - g * chunk)
+        lins = [torch.nn.Linear(D_in, H), torch.nn.Linear(H, H), torch.nn.Linear(H, H), torch.nn.Linear(H, P)]
+        with torch.no_grad():
+            lins[-1].weight *= out_scale
+            lins[-1].bias.fill_(out_bias)
+        for lst, l in zip([W1, W2, W3, W4], lins):
+            lst.append(l.weight.detach().numpy().copy())
+        for lst, l in zip([b1, b2, b3, b4], lins):
+            lst.append(l.bias.detach().numpy().copy())
+    xmin = np.array([3500.0, 0.0, -2.5, -0.2, 0.5][:D_in])
+    xmax = np.array([8000.0, 5.5, 0.5, 0.6, 3.0][:D_in])
+    return SpecNet(weights=[np.stack(W1), np.stack(W2), np.stack(W3), np.concatenate(W4, 0)],
+                   biases=[np.stack(b1), np.stack(b2), np.stack(b3), np.concatenate(b4, 0)],
+                   xmin=xmin, xmax=xmax, wavelength=np.asarray(wave, dtype=np.float64), resolution=float(resolution),
+                   inlabels=['teff', 'logg', 'feh', 'afe', 'vmic'][:D_in], encode_offset=0.0, nntype='MultiNet',
+                   chunk=int(chunk))
+
+
 def make_photnet(bands, H=128, seed=7):
     """Random-init per-band ``Net(6,H,1)`` (``photANN.py:21-26``), built band by band
     in list order so the reference harness can recreate the same modules."""
@@ -188,12 +223,15 @@ PROCYON_BANDS = ['Bessell_B', 'Bessell_V', 'Bessell_R', 'Bessell_I',
 def build_config(name, *, model_fn, ann_range=(5130.0, 5340.0), r_fwhm=50000.0,
                  obs_range=(5150.0, 5320.0), n_obs=7000, H=256, vmic=False,
                  npoly=0, bands=None, photscale=True, photH=128, vrot_max=5.0,
-                 snr=50.0, seed_net=0, seed_noise=3, obs_wave=None, nntype='LinNet'):
+                 snr=50.0, seed_net=0, seed_noise=3, obs_wave=None, nntype='LinNet', chunk=0):
     """Assemble a SynthConfig. ``model_fn(cfg, theta[1,ndim]) -> (flux[1,n_obs], mags)``
     supplies the noiseless model at the truth (the oracle, passed in by the caller so
     that this module has no dependency on ``oracle/``)."""
     wave, rsig = ann_wavegrid(ann_range[0], ann_range[1], r_fwhm)
-    spec = make_specnet(5 if vmic else 4, H, wave, rsig, seed=seed_net, nntype=nntype)
+    if nntype == 'MultiNet':
+        spec = make_multinet(5 if vmic else 4, H, wave, rsig, chunk, seed=seed_net)
+    else:
+        spec = make_specnet(5 if vmic else 4, H, wave, rsig, seed=seed_net, nntype=nntype)
     if obs_wave is None:
         obs_wave = np.linspace(obs_range[0], obs_range[1], n_obs)
     fit = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot']
@@ -273,6 +311,14 @@ def config_c1(model_fn, obs_wave=None, obs_flux=None, obs_phot=None, **kw):
     if obs_phot is not None:
         cfg.obs_phot = {b: [float(obs_phot[b][0]), float(obs_phot[b][1])] for b in cfg.phot.bands}
     return cfg
+
+
+def config_c4_chunked(model_fn, **kw):
+    """C4 (chunked variant): the full-wavelength emulator as G = 13 chunk nets
+    Net(5,512,512,512,P=4096) (last chunk 2632 pixels), everything else as config_c4."""
+    args = dict(nntype='MultiNet', chunk=4096)
+    args.update(kw)
+    return config_c4(model_fn, **args)
 
 
 def config_mini(model_fn, **kw):
