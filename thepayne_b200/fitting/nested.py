@@ -18,8 +18,8 @@ arrives one vector at a time.  What batches is the walk itself:
                      sampler); queued proposals are popped until one is still above the -- meanwhile
                      risen -- threshold (a point drawn uniformly inside an earlier, larger contour
                      and found inside the current one is uniform inside the current one);
-    adapt:           ``scale`` follows the walkers' acceptance fraction (target 0.5) like
-                     dynesty's ``update_rwalk``.
+    adapt:           ``scale`` follows the walkers' acceptance fraction (target 0.5) with dynesty's
+                     ``update_rwalk`` rule, applied after every lock-step move.
 
 ``sample()`` yields the same 15-tuple as ``dynesty.NestedSampler.sample`` so that the logging loop of
 fitstar.py:332-405 carries over; ``add_live_points()`` likewise.  dynesty itself is not installed in
@@ -133,6 +133,11 @@ class BatchedNestedSampler(object):
                 nacc[idx] += 1
                 nrej[ev[~ok]] += 1
             step += 1
+            # step size follows the acceptance fraction of THIS lock-step move (W outcomes at once: as much
+            # evidence as dynesty's per-proposal update_rwalk collects over W iterations)
+            facc = float(ok.sum()) / max(len(active), 1) if len(ev) else 0.0
+            norm = max(self.facc, 1.0 - self.facc) * self.ndim
+            self.scale = min(self.scale * math.exp((facc - self.facc) / norm), math.sqrt(self.ndim))
             if step >= self.walks:
                 # dynesty lets a walk that has not moved yet go on until it does; in lock-step those
                 # stragglers would arrive in calls of a handful of points, so by default
@@ -141,12 +146,6 @@ class BatchedNestedSampler(object):
                 if step >= self.walks * (1 + self.max_extra):
                     break
         self.f_inside = f_min
-        # acceptance-driven step size (dynesty update_rwalk)
-        tot = float(nacc.sum() + nrej.sum())
-        if tot > 0:
-            facc = nacc.sum() / tot
-            norm = max(self.facc, 1.0 - self.facc) * self.ndim
-            self.scale = min(self.scale * math.exp((facc - self.facc) / norm), math.sqrt(self.ndim))
         for i in range(W):
             if nacc[i] > 0:
                 self.queue.append((u[i], v[i], logl[i], int(nc[i])))
