@@ -37,6 +37,17 @@ def _worker(rank, world, port, B, q):
     loc = torch.full((5,), float(rank), dtype=torch.float64)
     g = gather_equal(loc)
     ok = ok and torch.equal(g, torch.arange(world, dtype=torch.float64).repeat_interleave(5))
+    # pipelined gather: results come back one submit later, in order, and flush() returns the rest
+    from thepayne_b200.dist import PipelinedGather
+    pg = PipelinedGather()
+    got = []
+    for step in range(4):
+        r = pg.submit(torch.full((3,), float(10 * step + rank), dtype=torch.float64))
+        if r is not None:
+            got.append(r.clone())
+    got += [r.clone() for r in pg.flush()]
+    want = [torch.tensor([10.0 * s + r for r in range(world) for _ in range(3)], dtype=torch.float64) for s in range(4)]
+    ok = ok and len(got) == 4 and all(torch.equal(a, b) for a, b in zip(got, want))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

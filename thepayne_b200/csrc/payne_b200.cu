@@ -275,6 +275,14 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   T.inv_dlnw = (double)(n - 1) / (std::log(w[n - 1]) - std::log(w[0]));
   T.sigma_in = kCkms / s->resolution;
   T.inst_scale = kFwhmFit;
+  {
+    // Opt-in ("1"): measured on B200 at C2 (sigma 3.8-5.6 px, 49-71 taps) the stencil's inner loop alone
+    // takes as long as the whole FFT convolution it replaces (tools/bench/stencil_bench.cu: 73 FMA/clk/SM
+    // as shipped, 106 with the coefficient loads removed; direct and FFT convolution need about the same
+    // flops at these widths), so the FFT stays the default.
+    const char* e = getenv("PAYNE_GAUSS_STENCIL");
+    T.gauss_stencil = (e && e[0] == '1');
+  }
   // log-uniform check (informational; enables the analytic regrid fast path later)
   double maxdev = 0.0;
   for (int i = 0; i < n; ++i)
@@ -454,7 +462,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     size_t win = 0;
     const char* wenv = getenv("PAYNE_ROT_WINDOW");            // "0": keep the table in L1/L2 only
     if (ok0 && occ0 >= 1 && !(wenv && wenv[0] == '0')) {
-      for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)10240, (size_t)8192, (size_t)6144,
+      for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)10240, (size_t)9216, (size_t)8448, (size_t)8192, (size_t)6144,
                           (size_t)4096, (size_t)2048}) {
         int o = 0;
         if (probe(c->tail_smem + cand, &o) && o == occ0) { win = cand; break; }
@@ -914,6 +922,8 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "max_batch") return c->slab;
   if (k == "sm_count") return c->sm_count;
   if (k == "tail_grid") return c->tail_grid;
+  if (k == "gauss_stencil") return c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
+  if (k == "rot_window_floats") return c->fast.win_floats;
   if (k == "precision") return c->lay.precision;
   if (k == "status") {
     int v = 0;
@@ -949,6 +959,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)
+  if (k == "gauss_stencil") { c->tail.gauss_stencil = value != 0; return PAYNE_OK; }
   if (k == "inst_r_is_sigma") { c->tail.inst_scale = value ? 1.0 : payne::kFwhmFit; return PAYNE_OK; }   // profiling aid, see tail.cuh
   return fail(PAYNE_E_INVALID, "unknown key " + k);
 }

@@ -74,6 +74,7 @@ struct TailParams {
   double* model_out;        // [B, n_obs] or null
   int* status;              // device flag: bit0 = a point needed a larger FFT than the carve-out
   int B;
+  int gauss_stencil;        // fast tail: instrumental broadening as a real-space stencil when the kernel is compact
   double inst_scale;        // Inst_R -> sigma-resolution: 2.355 (genmod.py:83, FWHM given) or 1 (getspec callers)
   int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
                             // bit3 the regrid back, bit4 the final pass; results are garbage
@@ -87,6 +88,7 @@ struct PointSetup {
   double du, rM;
   double lnD, u0t;      // u0t = ln w[i0] in the rest frame
   double poly[PAYNE_MAX_POLY];
+  double sig_px2;       // instrumental kernel variance in pixels^2 of the stage-2 grid
   float taper_a;        // exp(-a k^2)
   float hdu;
   int do_rot, use_inst, bad, i0, i1, log2N2, clean;
@@ -234,6 +236,7 @@ __device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S)
   const double dv = kCkms * S.du;                  // smoothing.py:282
   const double nd = (double)N2 * dv;
   S.taper_a = (float)(2.0 * CUDART_PI * CUDART_PI * s2 / (nd * nd));
+  S.sig_px2 = s2 / (dv * dv);
 }
 
 }  // namespace payne

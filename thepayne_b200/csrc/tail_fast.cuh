@@ -44,6 +44,9 @@ struct FastGrid {
 struct FastSetup {
   int s_incj, s_incr, s_den, s_num;   // stage 2: num = nM-1, den = N2-1, inc for pairs (2*256*num)
   float s_invden;
+  int st_R;                           // > 0: stage 2 is the real-space stencil of tail_stencil.cuh, half-width R
+  int st_e4, st_n4;                   // first coefficient step (in units of 4) and number of 4-step groups
+  double st_inv2s2;                   // 1 / (2 sigma_px^2)
   double q0, scale;                   // final: p = (obs_q - q0) * scale
 };
 
@@ -233,6 +236,10 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
   return acc;
 }
 
+}  // namespace payne
+#include "tail_stencil.cuh"
+namespace payne {
+
 // LOG2N1 <= 15: the whole transform sits in shared memory (3 CTAs/SM up to 2^14).
 // LOG2N1 == 16: split transform, half in shared memory (128 KB), half in the scratch line.
 template <int LOG2N1>
@@ -243,6 +250,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   float* zf = reinterpret_cast<float*>(smem_raw);
   __shared__ FastPoint SP;
   __shared__ double red[kNT / 32];
+  __shared__ StencilShared SS;
   PointSetup& S = SP.S;
   FastSetup& FS = SP.FS;
   const int tid = threadIdx.x;
@@ -307,7 +315,10 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       GaussH H{S.taper_a, 2.0f / (float)N2};
       bool split2 = false;
       if constexpr (kSplit) split2 = (log2N2 == LOG2N1);
-      if (split2) {
+      if (!kSplit && FS.st_R > 0) {
+        // compact Gaussian: circular real-space stencil instead of the second transform pair
+        acc = stage2_stencil(P, F, S, FS, zf, win, SS, row, tid, p);
+      } else if (split2) {
         if constexpr (kSplit) {
           stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
           __syncthreads();
@@ -390,6 +401,18 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
     FS.s_invden = 1.0f / (float)(N2 - 1);
     FS.scale = (double)(N2 - 1) / (double)(nM - 1);
     FS.q0 = (double)S.i0 + S.lnD * F.inv_dlnw;
+    // stencil instead of the FFT when the kernel is compact and resolved (tail_stencil.cuh); the signal
+    // must fit the shared-memory transform buffer (no split transforms) and fill whole chunks
+    const double spx = sqrt(S.sig_px2);
+    const int R = (int)ceil(kStSigmas * spx);
+    if (P.gauss_stencil && spx >= kStMinSigmaPx && R <= kStMaxR && S.log2N2 >= 11 && S.log2N2 <= 15 &&
+        F.win_floats >= kStSideFloats) {
+      const int E = (R + 2) / 2;                       // offsets 2e-1, 2e, 2e+1 must cover [-R, R]
+      FS.st_R = R;
+      FS.st_e4 = -((E + 3) / 4);
+      FS.st_n4 = (E - 4 * FS.st_e4) / 4 + 1;
+      FS.st_inv2s2 = 0.5 / S.sig_px2;
+    }
   }
   out->S = S;
   out->FS = FS;
