@@ -17,6 +17,10 @@
  *                           FastPayneSEDPredict.sed        Payne/predict/predictsed.py:75-103
  *   payne_ann_eval          ANN.eval / LinNet.forward      Payne/predict/predictspec.py:61-74,
  *                                                          Payne/train/NNmodels.py:154-168
+ *   payne_ctx_attach_continuum  PayneSpecPredict(Cnnpath=...) / predictcont + the continuum multiply of getspec
+ *                                                          Payne/predict/predictspec.py:96-102,122-134,208-226
+ *   payne_ctx_set_lsf       getspec(inst_R=<vector>)       Payne/predict/predictspec.py:265-286 ->
+ *                           smoothspec(smoothtype='lsf')   Payne/utils/smoothing.py:126-150,482-586
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a
  * negative PAYNE_E_* code and never throws; payne_last_error() gives the message of the
@@ -40,7 +44,7 @@
 extern "C" {
 #endif
 
-#define PAYNE_ABI_VERSION 3
+#define PAYNE_ABI_VERSION 4
 
 enum {
   PAYNE_OK = 0,
@@ -156,13 +160,27 @@ int payne_lnlike_batch_host(PayneCtx* ctx, const double* theta_host, int64_t B, 
 int payne_model_batch(PayneCtx* ctx, const double* theta_dev, int64_t B, int64_t ld,
                       double* flux_dev, double* mags_dev, double* lnl_dev, void* stream);
 
+/* Continuum emulator (HOST pointers, copied): any PayneSpecNet the spectrum emulator could be; its
+ * `wavelength` is the continuum's own grid.  From then on every model spectrum is multiplied, right after
+ * the emulator and before any broadening, by np.interp(modwave, contwave, c / nanmedian(c), left=nan,
+ * right=nan) with c = F_nu -> F_lambda of the continuum net's output (predictspec.py:208-226).  Attaching
+ * again replaces the previous one.  Not reachable from the likelihood (it never passes Cnnpath). */
+int payne_ctx_attach_continuum(PayneCtx* ctx, const PayneSpecNet* cont);
+
+/* LSF vector: lsf_host[n_obs] = dispersion (sigma, in AA) at every observed pixel.  While set, the
+ * instrumental stage is smooth_lsf_fft (smoothing.py:482-586) instead of the scalar-R Gaussian and the
+ * Inst_R parameter is ignored; observed pixels outside the emulator's coverage take the edge value (the
+ * reference's np.interp clamps there) instead of NaN.  NULL switches back.  Emulator grids up to 32768
+ * pixels; a point whose cdf grid would need more than 32768 samples returns NaN and sets status bit 0. */
+int payne_ctx_set_lsf(PayneCtx* ctx, const double* lsf_host, int64_t n);
+
 /* Emulator forward pass only.  x_dev: [B, D_in] fp64 labels; y_dev: [B, ldy] fp32, ldy>=D_out.
  * Tensor-core precisions write y with TMA stores: y_dev 16-byte aligned, ldy a multiple of 4. */
 int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, int64_t ldy,
                    void* stream);
 
 /* Introspection for benches/tests: key is one of "n_ann","n_obs","nfft1","launches",
- * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","status"
+ * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","continuum","lsf","status"
  * (bit0: a point needed a larger transform than the shared-memory carve-out). Returns the value or -1. */
 int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
 /* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points), "timing" (0/1,

@@ -116,3 +116,33 @@ def thetas(name, cfg):
         put(10, 'Vrot', 0.3)
         put(11, 'Vrad', 250.0)           # mask endpoints move by ~40 px
     return th
+
+
+# --------------------------------------------------------------------------- getspec-only branches
+def getspec_case():
+    """Inputs of the ``f3_getspec`` fixture: the two ``getspec`` branches the likelihood never reaches --
+    the continuum emulator (``Cnnpath``, predictspec.py:96-102, 208-226) and the LSF vector
+    (predictspec.py:265-286).  Returns (spec, cont, calls); every call is a keyword dictionary for
+    ``PayneSpecPredict.getspec`` plus ``use_cont``."""
+    wave, rsig = synth.ann_wavegrid(5140.0, 5190.0, 50000.0)
+    spec = synth.make_specnet(4, 64, wave, rsig, seed=0)
+    # the continuum net has its own, coarser grid that stops short of the red end of the spectrum's:
+    # pixels beyond it are NaN after the multiply (np.interp right=nan)
+    cwave = np.linspace(5135.0, 5178.0, 301)
+    cont = synth.make_specnet(4, 32, cwave, rsig, seed=5)
+    outwave = np.linspace(5150.0, 5180.0, 1500)
+    lsf = 0.070 + 0.012 * (outwave - 5150.0) / 30.0 + 0.002 * np.sin((outwave - 5150.0) / 3.0)
+    wave_r = wave * (1.0 + (12.0 / 299792.458))
+    lsf_native = 0.080 + 0.010 * (wave_r - wave_r[0]) / (wave_r[-1] - wave_r[0])
+    sun = {'Teff': 5770.0, 'log(g)': 4.44, '[Fe/H]': 0.0, '[a/Fe]': 0.0}
+    cool = {'Teff': 4600.0, 'log(g)': 4.7, '[Fe/H]': -0.08, '[a/Fe]': 0.05}
+    calls = [
+        dict(sun, rot_vel=3.0, rad_vel=0.5, inst_R=32000.0 * 2.355, outwave=outwave, use_cont=True),
+        dict(cool, rot_vel=0.0, rad_vel=-25.0, outwave=outwave, use_cont=True),            # plain interp: NaN red end
+        dict(cool, rot_vel=8.0, rad_vel=0.0, inst_R=30000.0 * 2.355, outwave=None, use_cont=True),
+        dict(sun, rot_vel=3.0, rad_vel=0.5, inst_R=lsf, outwave=outwave, use_cont=False),
+        dict(cool, rot_vel=0.0, rad_vel=0.0, inst_R=lsf, outwave=outwave, use_cont=False),
+        dict(sun, rot_vel=15.0, rad_vel=-60.0, inst_R=1.4 * lsf, outwave=outwave, use_cont=True),
+        dict(sun, rot_vel=2.0, rad_vel=12.0, inst_R=lsf_native, outwave=None, use_cont=False),
+    ]
+    return spec, cont, calls

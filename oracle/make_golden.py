@@ -51,8 +51,24 @@ def prior_golden():
     print('prior', theta.shape, 'finite', int(np.isfinite(theta).all()), 'lnp[:3]', lnp[:3])
 
 
+def getspec_golden():
+    """``f3_getspec``: the reference's getspec with a continuum emulator / an LSF vector."""
+    spec, cont, calls = goldens.getspec_case()
+    d = dict(digest=np.array(spec.digest()), cdigest=np.array(cont.digest()))
+    for i, kw in enumerate(calls):
+        kw = dict(kw)
+        use_cont = kw.pop('use_cont')
+        (w, f), = refharness.ref_getspec(spec, cont if use_cont else None, [kw])
+        d['wave_%d' % i], d['flux_%d' % i] = w, f
+        print('f3_getspec call', i, 'n', len(f), 'nan', int(np.isnan(f).sum()), 'mean', np.nanmean(f))
+    np.savez_compressed(os.path.join(OUT, 'f3_getspec.npz'), **d)
+
+
 if __name__ == '__main__':
-    names = sys.argv[1:] or (list(goldens.CASES) + ['prior'])
+    names = sys.argv[1:] or (list(goldens.CASES) + ['prior', 'f3_getspec'])
+    if 'f3_getspec' in names:
+        names.remove('f3_getspec')
+        getspec_golden()
     if 'prior' in names:
         names.remove('prior')
         prior_golden()

@@ -204,6 +204,8 @@ def smooth_R(wave, spec, rsigma, outwave, inres_rsigma):
     m = _mask(wave, rsigma, outwave)
     w = wave[m]
     s = np.nan_to_num(spec[m], nan=1.0)
+    if outwave is None:                                      # smoothing.py:140-141
+        outwave = wave
     with np.errstate(invalid='ignore'):
         sigma = np.sqrt(sigma_out ** 2 - inres ** 2)
     wn, sn = _resample_pow2(w, s)
@@ -214,17 +216,55 @@ def smooth_R(wave, spec, rsigma, outwave, inres_rsigma):
     return np.interp(outwave, wn, conv, right=np.nan, left=np.nan)
 
 
+def smooth_lsf(wave, spec, disp, outwave):
+    """``smoothspec(type='lsf', fftsmooth=True)``: ``smoothing.py:126-150`` (linear mask of
+    ``20 * 100`` AA, ``sigma = resolution[mask]``), ``482-586`` (smooth_lsf_fft) and ``588-608``
+    (smooth_fft).  ``disp``: dispersion in AA at every pixel of ``wave``."""
+    if outwave is not None:
+        wlim = np.array([outwave.min(), outwave.max()])
+    else:
+        wlim = np.squeeze(np.array([0, np.inf]))
+    wlim = wlim + 20.0 * 100 * np.array([-1, 1])
+    m = (wave > wlim[0]) & (wave < wlim[1])
+    w = wave[m]
+    s = np.nan_to_num(spec[m], nan=1.0)
+    if outwave is None:
+        outwave = wave
+    sigma = disp[m]
+    dw = np.gradient(w)
+    cdf = np.cumsum(dw / sigma)
+    cdf /= cdf.max()
+    x_per_sigma = np.nanmedian(np.gradient(cdf) / (dw / sigma))
+    N = 2 / x_per_sigma
+    nx = int(2 ** np.ceil(np.log2(N)))
+    x = np.linspace(0, 1, nx)
+    dx = 1.0 / nx
+    lam = np.interp(x, cdf, w)
+    newspec = np.interp(lam, w, s)
+    ss = np.fft.rfftfreq(len(newspec), d=dx)
+    taper = np.exp(-2 * (np.pi ** 2) * (x_per_sigma ** 2) * (ss ** 2))
+    conv = np.fft.irfft(np.fft.rfft(newspec) * taper)
+    return np.interp(outwave, lam, conv)
+
+
 # --------------------------------------------------------------------------- getspec
 def getspec(net_fwd, spec, teff, logg, feh, afe, vmic, rot_vel, rad_vel, inst_R,
-            outwave, mlp_flux=None):
-    """``predictspec.py:136-294`` for scalar ``inst_R`` (no continuum ANN, no LSF).
-    ``inst_R`` is already the sigma-R the caller passes (``genmod.py:82-85``)."""
+            outwave, mlp_flux=None, cont=None):
+    """``predictspec.py:136-294``.  ``inst_R`` is the sigma-R the caller passes (``genmod.py:82-85``) or,
+    when not a float, the LSF vector of ``:265-286``; ``cont = (cont_fwd, cont_spec)`` is the continuum
+    emulator of ``:96-102, 208-226``; ``outwave`` may be None (native grid, ``:290-292``)."""
     if np.isfinite(vmic):
         labels = [teff, logg, feh, afe, vmic]              # :188-204
     else:
         labels = [teff, logg, feh, afe]
     modspec = net_fwd(np.asarray(labels)).squeeze() if mlp_flux is None else mlp_flux
     modwave = spec.wavelength
+    if cont is not None:                                     # :208-226
+        cfwd, cspec = cont
+        modcont = cfwd(np.asarray(labels)).squeeze()
+        modcont = modcont * (SPEEDOFLIGHT / ((cspec.wavelength * 1E-8) ** 2.0))
+        modcont = modcont / np.nanmedian(modcont)
+        modspec = modspec * np.interp(modwave, cspec.wavelength, modcont, right=np.nan, left=np.nan)
     if rot_vel != 0.0:                                       # :228-241
         modspec = smooth_vsini(modwave, modspec, rot_vel)
         modspec[0] = modspec[1]
@@ -232,12 +272,18 @@ def getspec(net_fwd, spec, teff, logg, feh, afe, vmic, rot_vel, rad_vel, inst_R,
     if rad_vel != 0.0:                                       # :243-249
         modwave = modwave * (1.0 + (rad_vel / SPEEDOFLIGHT))
     done = False
-    if isinstance(inst_R, float) and inst_R > 0.0:           # :255-263
-        modspec = smooth_R(modwave, modspec, inst_R, outwave, spec.resolution)
+    if isinstance(inst_R, float):
+        if inst_R > 0.0:                                     # :255-263
+            modspec = smooth_R(modwave, modspec, inst_R, outwave, spec.resolution)
+            done = True
+    else:                                                    # :265-286
+        disparr = np.interp(modwave, outwave, inst_R) if outwave is not None else np.asarray(inst_R)
+        assert len(disparr) == len(modwave)
+        modspec = smooth_lsf(modwave, modspec, disparr, outwave)
         done = True
-    if not done:                                             # :288-289
+    if not done and outwave is not None:                     # :288-289
         modspec = np.interp(outwave, modwave, modspec, right=np.nan, left=np.nan)
-    return outwave, modspec
+    return (outwave if outwave is not None else modwave), modspec
 
 
 def polycalc(coef, inwave):

@@ -208,6 +208,47 @@ def build_likelihood(cfg):
     return like
 
 
+def _ref_ann(R, s):
+    """Reference ``ANN`` (predictspec.py:29-74) around a random-init LinNet / SMLP container."""
+    nntype = getattr(s, 'nntype', 'LinNet')
+    if nntype == 'SMLP':
+        H1, H2, H3 = [w.shape[0] for w in s.weights[:3]]
+        model = R.NNmodels.SMLP(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
+        sd = {}
+        for k in range(4):
+            sd['features.%d.weight' % (2 * k)] = torch.from_numpy(s.weights[k].copy())
+            sd['features.%d.bias' % (2 * k)] = torch.from_numpy(s.biases[k].copy())
+    else:
+        H1, H2, H3 = s.weights[0].shape[0], s.weights[3].shape[0], s.weights[4].shape[0]
+        model = R.NNmodels.LinNet(s.D_in, H1, H2, H3, s.D_out, s.xmin, s.xmax)
+        sd = {}
+        for k in range(6):
+            sd['lin%d.weight' % (k + 1)] = torch.from_numpy(s.weights[k].copy())
+            sd['lin%d.bias' % (k + 1)] = torch.from_numpy(s.biases[k].copy())
+    model.load_state_dict(sd)
+    model.eval()
+    model.D_in = s.D_in
+    ann = R.predictspec.ANN.__new__(R.predictspec.ANN)
+    ann.model, ann.wavelength = model, s.wavelength.copy()
+    ann.resolution = np.array(s.resolution, dtype=float)
+    ann.xmin, ann.xmax, ann.inlabels, ann.NNtype = s.xmin, s.xmax, s.inlabels, nntype
+    return ann
+
+
+def ref_getspec(spec, cont, calls):
+    """Reference ``PayneSpecPredict.getspec`` (predictspec.py:136-294) with an optional continuum emulator
+    (``Canns``, :96-102); ``calls`` = list of keyword dictionaries, returns the list of (wave, flux)."""
+    R = load()
+    PP = R.predictspec.PayneSpecPredict.__new__(R.predictspec.PayneSpecPredict)
+    PP.anns, PP.NN, PP.NNtype = _ref_ann(R, spec), {}, getattr(spec, 'nntype', 'LinNet')
+    PP.Canns = _ref_ann(R, cont) if cont is not None else None
+    out = []
+    for kw in calls:
+        w, f = PP.getspec(**kw)
+        out.append((np.array(w, dtype=np.float64), np.array(f, dtype=np.float64)))
+    return out
+
+
 def ref_model(cfg, theta):
     """Reference model spectrum/mags for each row of theta (via genspec/genphot*)."""
     like = build_likelihood(cfg)

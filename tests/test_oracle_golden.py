@@ -49,3 +49,21 @@ def test_batched_mlp_noise_floor():
     rel = np.nanmax(np.abs(fa - fb) / np.abs(fa))
     assert rel < 1e-6
     assert np.max(np.abs(a[ok] - b[ok])) < 5e-3
+
+
+def test_oracle_getspec_continuum_and_lsf_match_reference():
+    """the continuum-emulator multiply (predictspec.py:208-226) and the LSF-vector
+    broadening (predictspec.py:265-286 -> smoothing.py:482-586) against the unmodified reference's getspec."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'f3_getspec.npz'))
+    spec, cont, calls = goldens.getspec_case()
+    assert spec.digest() == str(g['digest']) and cont.digest() == str(g['cdigest'])
+    net, cnet = O.make_net(spec), O.make_net(cont)
+    for i, kw in enumerate(calls):
+        w, f = O.getspec(net, spec, kw['Teff'], kw['log(g)'], kw['[Fe/H]'], kw['[a/Fe]'], np.nan, kw['rot_vel'],
+                         kw['rad_vel'], kw.get('inst_R', np.nan), kw['outwave'],
+                         cont=(cnet, cont) if kw['use_cont'] else None)
+        np.testing.assert_array_equal(w, g['wave_%d' % i])
+        np.testing.assert_allclose(f, g['flux_%d' % i], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.isnan(g['flux_1']).sum() > 50          # plain-interp call: pixels beyond the continuum grid are NaN

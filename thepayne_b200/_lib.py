@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpayne_b200.so')
 
-ABI_VERSION = 3          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
+ABI_VERSION = 4          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
 NPAR = 13
 MAX_POLY = 16
 PAR_INDEX = {
@@ -22,7 +22,8 @@ PREC = {'parity': 0, 'x3': 0, 'tf32': 1, 'bf16': 2, 'simt': 3, 'fp32': 3, '3xtf3
 
 EXPORTS = ['payne_abi_version', 'payne_last_error', 'payne_ctx_create', 'payne_ctx_destroy',
            'payne_lnlike_batch', 'payne_lnlike_batch_host', 'payne_model_batch', 'payne_ann_eval',
-           'payne_ctx_query', 'payne_ctx_set', 'payne_ctx_last_ms', 'payne_gemm_test']
+           'payne_ctx_query', 'payne_ctx_set', 'payne_ctx_last_ms', 'payne_gemm_test',
+           'payne_ctx_attach_continuum', 'payne_ctx_set_lsf']
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)
@@ -90,6 +91,10 @@ def load():
     lib.payne_model_batch.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp]
     lib.payne_ann_eval.restype = C.c_int
     lib.payne_ann_eval.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp]
+    lib.payne_ctx_attach_continuum.restype = C.c_int
+    lib.payne_ctx_attach_continuum.argtypes = [vp, C.POINTER(PayneSpecNet)]
+    lib.payne_ctx_set_lsf.restype = C.c_int
+    lib.payne_ctx_set_lsf.argtypes = [vp, vp, C.c_int64]
     lib.payne_ctx_query.restype = C.c_int64
     lib.payne_ctx_query.argtypes = [vp, C.c_char_p]
     lib.payne_ctx_set.restype = C.c_int

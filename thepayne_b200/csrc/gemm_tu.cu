@@ -1,0 +1,38 @@
+// Translation unit of the tcgen05 GEMM templates (mlp_tc.cuh); see launchers.h.
+#include "launchers.h"
+
+namespace payne {
+
+int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
+                    const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
+                    float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                    TcMapCache* caches, long long out_rows) {
+  return tc_run_layers(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift, prec, sm_count, st,
+                       launches, caches, out_rows);
+}
+
+int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,
+                      TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out, long long ldo,
+                      float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                      long long out_rows) {
+  return tc_run_multinet(tcw, bias, H, D_out, groups, chunk, actA, actB, rows_per_group, nb, out, ldo, bias_shift,
+                         prec, sm_count, st, launches, out_rows);
+}
+
+int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& a, const TcWeights& w,
+                   const float* db, float* dC, int sm_count) {
+  const unsigned blocks = (unsigned)(((long long)M * K + 255) / 256);
+  if (precision == PAYNE_PREC_PARITY) {
+    x3_split_kernel<<<blocks, 256>>>(dA, K, (__nv_bfloat16*)a.plane[0], (__nv_bfloat16*)a.plane[1],
+                                     (__nv_bfloat16*)a.plane[2], a.ld, M, K);
+    return tc_launch<128, kModeX3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, sm_count, 0);
+  }
+  tf32_split_kernel<<<blocks, 256>>>(dA, K, (float*)a.plane[0], (float*)a.plane[1], a.ld, M, K);
+  if (precision == PAYNE_PREC_3XTF32)
+    return tc_launch<128, kModeT3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, sm_count, 0);
+  if (precision == PAYNE_PREC_TF32)
+    return tc_launch<128, kModeT1, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, sm_count, 0);
+  return PAYNE_E_UNSUPPORTED;
+}
+
+}  // namespace payne

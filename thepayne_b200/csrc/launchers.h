@@ -1,0 +1,40 @@
+// Plain-function front doors of the heavy kernel templates.  Each family of templates is instantiated
+// in its own translation unit (gemm_tu.cu, tail_fast_tu.cu, tail_general_tu.cu) so that the library
+// builds in parallel; payne_b200.cu holds the host logic and the small kernels and calls through here.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mlp_tc.cuh"
+#include "tail_fast.cuh"
+#include "tail_lsf.cuh"
+
+namespace payne {
+
+// ---- gemm_tu.cu: lin2..lin6 on tcgen05 (mlp_tc.cuh)
+int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
+                    const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
+                    float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                    TcMapCache* caches, long long out_rows);
+int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,
+                      TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out, long long ldo,
+                      float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
+                      long long out_rows);
+// unit-test GEMM: slices dA [M, K] into the operand planes of `a`, then C = A . W^T + bias
+int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& a, const TcWeights& w,
+                   const float* dbias, float* dC, int sm_count);
+
+// ---- tail_fast_tu.cu: fused tail on log-uniform grids (tail_fast.cuh)
+// sets the dynamic shared-memory opt-in of tail_fast_kernel<l2> on the current device and reports the
+// resident CTAs per SM; false when the kernel does not exist for l2 or the query fails
+bool probe_tail_fast(int l2, size_t smem_bytes, int* ctas_per_sm);
+int launch_tail_fast(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+int launch_tail_setup(int nb, cudaStream_t st, const TailParams& T, const FastGrid& F);
+
+// ---- tail_general_tu.cu: any increasing grid (tail_general.cuh), LSF-vector broadening (tail_lsf.cuh)
+bool probe_tail_general(int l2, size_t smem_bytes, int* ctas_per_sm);
+int launch_tail_general(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const TwConst& tc);
+bool probe_tail_lsf(size_t smem_bytes, int* ctas_per_sm);
+int launch_tail_lsf(int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const LsfParams& L);
+int launch_continuum(int grid, cudaStream_t st, const ContParams& C);
+
+}  // namespace payne

@@ -33,7 +33,7 @@ struct EncodeParams {
 };
 
 // h1[p, h] = sigmoid(W1[h, :] . enc(x_p) + b1[h]); optionally also the tf32 hi/lo split planes.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 encode_layer1_kernel(const __grid_constant__ EncodeParams E, const double* __restrict__ x, long long ld,
                      const float* __restrict__ W1, const float* __restrict__ b1, float* __restrict__ out,
                      long long ldo, int B) {

@@ -837,7 +837,7 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemm
 }
 
 // fp32 -> operand planes of the next GEMM
-__global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, float* __restrict__ hi,
+static __global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, float* __restrict__ hi,
                                   float* __restrict__ lo, long long ldd, long long rows, int cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
@@ -847,7 +847,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, 
   hi[r * ldd + c] = h;
   lo[r * ldd + c] = ptx::to_tf32(x - h);
 }
-__global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ p1,
+static __global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ p1,
                                 __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldd,
                                 long long rows, int cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -862,7 +862,7 @@ __global__ void x3_split_kernel(const float* __restrict__ src, long long lds, __
 // Lane i < D_in encodes label i once (fp64, NNmodels.py:164-168) and the warp shares the result;
 // each lane then forms outputs h = lane, lane + 32, ... with the same fmaf order as
 // encode_layer1_kernel and writes the three bf16 planes that lin2 reads.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 encode_layer1_x3_kernel(const __grid_constant__ EncodeParams E, const double* __restrict__ x, long long ld,
                         const float* __restrict__ W1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ p1,
                         __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldp, int B,

@@ -13,11 +13,9 @@
 #include <cuda_runtime.h>
 
 #include "../../include/payne_b200.h"
-#include "mlp_simt.cuh"
-#include "mlp_tc.cuh"
+#include "launchers.h"
 #include "phot.cuh"
-#include "tail.cuh"
-#include "tail_fast.cuh"
+#include "continuum.cuh"
 
 namespace {
 
@@ -148,6 +146,15 @@ struct PayneCtx {
   int grid_loguniform = 0;
   int use_fast = 0;        // analytic-regrid tail selected (log-uniform emulator grid)
   int allow_fast = 1;
+  // continuum emulator (predictspec.py:96-102, 208-226): a second emulator context (weights, operand
+  // planes, its own output rows) and the per-dataset tables of the multiply
+  PayneCtx* cont = nullptr;
+  payne::ContParams contp{};
+  // LSF vector (predictspec.py:265-286): replaces the scalar-R stage of the tail
+  bool lsf_on = false;
+  payne::LsfParams lsf{};
+  size_t lsf_smem = 0;
+  int lsf_grid = 0;
   // photometry
   bool has_phot = false;
   payne::PhotParams phot{};
@@ -204,60 +211,11 @@ int upload_owned(PayneCtx* c, T** dst, const T* src, size_t n) {
   return rc;
 }
 
-int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
+// Per-dataset tables of the fused tail: emulator grid, stage-1 regrid tables, rotation-kernel table,
+// twiddles, observation arrays, analytic regrid constants, kernel occupancy.
+int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   using namespace payne;
-  c->D_in = s->D_in; c->H[0] = s->H1; c->H[1] = s->H2; c->H[2] = s->H3; c->D_out = s->D_out;
-  if (s->D_in < 1 || s->D_in > 8) return fail(PAYNE_E_INVALID, "D_in must be in [1,8]");
-  if (s->D_out < 32) return fail(PAYNE_E_INVALID, "D_out must be >= 32");
-  const int nl = s->n_layers == 0 ? 6 : s->n_layers;
-  if (nl != 6 && nl != 4 && nl != 3) return fail(PAYNE_E_INVALID, "n_layers must be 6 (LinNet), 4 (SMLP / multi-chunk) or 3 (YST1)");
-  c->multinet = (nl == 4 && s->activation == PAYNE_ACT_SIGMOID && s->n_groups >= 1);
-  if (!c->multinet && (nl == 6) != (s->activation == PAYNE_ACT_SIGMOID))
-    return fail(PAYNE_E_UNSUPPORTED, "supported emulators: 6 sigmoid layers, 4 sigmoid layers in chunks, or 3/4 leaky-ReLU layers");
-  c->n_layers = nl;
-  c->legacy = (nl != 6) && !c->multinet;
-  if (c->multinet) {
-    c->n_groups = s->n_groups; c->chunk = s->group_size;
-    if (c->chunk < 32 || (long long)(c->n_groups - 1) * c->chunk >= s->D_out || (long long)c->n_groups * c->chunk < s->D_out)
-      return fail(PAYNE_E_INVALID, "multi-chunk emulator: n_groups chunks of group_size pixels must tile D_out (last one may be narrower)");
-    if (s->H2 != s->H1 || s->H3 != s->H1) return fail(PAYNE_E_INVALID, "multi-chunk emulator: H2 and H3 must equal H1");
-    if (c->n_groups > 64) return fail(PAYNE_E_UNSUPPORTED, "at most 64 chunk nets");
-  }
-  int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
-  int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
-  if (nl == 4) {                                   // NNmodels.py:99-107
-    const int a[4] = {s->D_in, s->H1, s->H2, s->H3}, b[4] = {s->H1, s->H2, s->H3, s->D_out};
-    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
-  } else if (nl == 3) {                            // ystpred.py:25-30
-    const int a[3] = {s->D_in, s->H1, s->H2}, b[3] = {s->H1, s->H2, s->D_out};
-    for (int k = 0; k < 3; ++k) { din[k] = a[k]; dout[k] = b[k]; }
-  }
-  if (c->multinet) {
-    // stacked over the chunks: [G*H, D_in], [G*H, H], [G*H, H], [D_out, H]
-    const int G = c->n_groups, H = s->H1;
-    const int a[4] = {s->D_in, H, H, H}, b[4] = {G * H, G * H, G * H, s->D_out};
-    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
-  }
-  for (int k = 0; k < nl; ++k) {
-    c->dims_in[k] = din[k]; c->dims_out[k] = dout[k];
-    int rc = upload_owned(c, &c->W[k], s->W[k], (size_t)din[k] * dout[k]);
-    if (rc) return rc;
-    rc = upload_owned(c, &c->b[k], s->b[k], (size_t)dout[k]);
-    if (rc) return rc;
-  }
   EncodeParams& E = c->enc;
-  E.D_in = s->D_in; E.H1 = s->H1; E.offset = s->encode_offset;
-  E.cast32 = (nl == 6 || c->multinet) ? 1 : (s->label_fp32_cast != 0);
-  E.act = c->legacy ? kActLeaky : kActSigmoid;
-  const int label_par[5] = {PAYNE_P_TEFF, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VMIC};
-  for (int i = 0; i < 8; ++i) {
-    E.col[i] = -1; E.fixed[i] = std::numeric_limits<double>::quiet_NaN(); E.xmin[i] = 0; E.xmax[i] = 1;
-  }
-  for (int i = 0; i < s->D_in; ++i) {
-    E.xmin[i] = s->xmin[i]; E.xmax[i] = s->xmax[i];
-    if (i < 5) { E.col[i] = c->lay.col[label_par[i]]; E.fixed[i] = c->lay.fixed[label_par[i]]; }
-  }
-
   // ---- emulator grid
   const int n = s->D_out;
   std::vector<double> w(s->wavelength, s->wavelength + n), inv_dw(n - 1);
@@ -441,22 +399,7 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     // costs one wavefront instead of one per touched line).  Take the largest slice that does not
     // cost a resident CTA.
     int occf = 0;
-    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-    auto probe = [&](size_t bytes, int* occ) {
-#define PAYNE_FAST_CASE(L)                                                                           \
-      case L:                                                                                        \
-        e1 = cudaFuncSetAttribute(payne::tail_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)bytes);                                                       \
-        e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, payne::tail_fast_kernel<L>, payne::kNT, bytes); \
-        break;
-      switch (l2) {
-        PAYNE_FAST_CASE(10) PAYNE_FAST_CASE(11) PAYNE_FAST_CASE(12) PAYNE_FAST_CASE(13)
-        PAYNE_FAST_CASE(14) PAYNE_FAST_CASE(15) PAYNE_FAST_CASE(16)
-        default: break;
-      }
-#undef PAYNE_FAST_CASE
-      return e1 == cudaSuccess && e2 == cudaSuccess;
-    };
+    auto probe = [&](size_t bytes, int* occ) { return payne::probe_tail_fast(l2, bytes, occ); };
     int occ0 = 0;
     const bool ok0 = probe(c->tail_smem, &occ0);
     size_t win = 0;
@@ -466,7 +409,6 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
                           (size_t)4096, (size_t)2048}) {
         int o = 0;
         if (probe(c->tail_smem + cand, &o) && o == occ0) { win = cand; break; }
-        e1 = e2 = cudaSuccess;
       }
     }
     c->fast_smem = c->tail_smem + win;
@@ -482,26 +424,74 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   }
   if (l2 <= 15) {
     int occ = 0;
-    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-#define PAYNE_GEN_CASE(L)                                                                              \
-    case L:                                                                                            \
-      e1 = cudaFuncSetAttribute(payne::tail_general_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                (int)c->tail_smem);                                                    \
-      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, payne::tail_general_kernel<L>,          \
-                                                         payne::kTailThreads, c->tail_smem);           \
-      break;
-    switch (l2 < 10 ? 10 : l2) {
-      PAYNE_GEN_CASE(10) PAYNE_GEN_CASE(11) PAYNE_GEN_CASE(12) PAYNE_GEN_CASE(13) PAYNE_GEN_CASE(14)
-      PAYNE_GEN_CASE(15)
-      default: break;
-    }
-#undef PAYNE_GEN_CASE
-    if (e1 != cudaSuccess || e2 != cudaSuccess || occ < 1)
+    if (!payne::probe_tail_general(l2, c->tail_smem, &occ) || occ < 1)
       return fail(PAYNE_E_UNSUPPORTED, "tail kernel does not fit on an SM");
     c->tail_grid = occ * c->sm_count;
   } else if (!c->use_fast) {
     return fail(PAYNE_E_UNSUPPORTED,
                 "a 65536-point transform needs the log-uniform fast tail (emulator grid is not log-uniform)");
+  }
+  return PAYNE_OK;
+}
+
+int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs, bool emulator_only = false) {
+  using namespace payne;
+  c->D_in = s->D_in; c->H[0] = s->H1; c->H[1] = s->H2; c->H[2] = s->H3; c->D_out = s->D_out;
+  if (s->D_in < 1 || s->D_in > 8) return fail(PAYNE_E_INVALID, "D_in must be in [1,8]");
+  if (s->D_out < 32) return fail(PAYNE_E_INVALID, "D_out must be >= 32");
+  const int nl = s->n_layers == 0 ? 6 : s->n_layers;
+  if (nl != 6 && nl != 4 && nl != 3) return fail(PAYNE_E_INVALID, "n_layers must be 6 (LinNet), 4 (SMLP / multi-chunk) or 3 (YST1)");
+  c->multinet = (nl == 4 && s->activation == PAYNE_ACT_SIGMOID && s->n_groups >= 1);
+  if (!c->multinet && (nl == 6) != (s->activation == PAYNE_ACT_SIGMOID))
+    return fail(PAYNE_E_UNSUPPORTED, "supported emulators: 6 sigmoid layers, 4 sigmoid layers in chunks, or 3/4 leaky-ReLU layers");
+  c->n_layers = nl;
+  c->legacy = (nl != 6) && !c->multinet;
+  if (c->multinet) {
+    c->n_groups = s->n_groups; c->chunk = s->group_size;
+    if (c->chunk < 32 || (long long)(c->n_groups - 1) * c->chunk >= s->D_out || (long long)c->n_groups * c->chunk < s->D_out)
+      return fail(PAYNE_E_INVALID, "multi-chunk emulator: n_groups chunks of group_size pixels must tile D_out (last one may be narrower)");
+    if (s->H2 != s->H1 || s->H3 != s->H1) return fail(PAYNE_E_INVALID, "multi-chunk emulator: H2 and H3 must equal H1");
+    if (c->n_groups > 64) return fail(PAYNE_E_UNSUPPORTED, "at most 64 chunk nets");
+  }
+  int din[6] = {s->D_in, s->H1, s->H1, s->H2, s->H2, s->H3};
+  int dout[6] = {s->H1, s->H1, s->H2, s->H2, s->H3, s->D_out};
+  if (nl == 4) {                                   // NNmodels.py:99-107
+    const int a[4] = {s->D_in, s->H1, s->H2, s->H3}, b[4] = {s->H1, s->H2, s->H3, s->D_out};
+    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  } else if (nl == 3) {                            // ystpred.py:25-30
+    const int a[3] = {s->D_in, s->H1, s->H2}, b[3] = {s->H1, s->H2, s->D_out};
+    for (int k = 0; k < 3; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  }
+  if (c->multinet) {
+    // stacked over the chunks: [G*H, D_in], [G*H, H], [G*H, H], [D_out, H]
+    const int G = c->n_groups, H = s->H1;
+    const int a[4] = {s->D_in, H, H, H}, b[4] = {G * H, G * H, G * H, s->D_out};
+    for (int k = 0; k < 4; ++k) { din[k] = a[k]; dout[k] = b[k]; }
+  }
+  for (int k = 0; k < nl; ++k) {
+    c->dims_in[k] = din[k]; c->dims_out[k] = dout[k];
+    int rc = upload_owned(c, &c->W[k], s->W[k], (size_t)din[k] * dout[k]);
+    if (rc) return rc;
+    rc = upload_owned(c, &c->b[k], s->b[k], (size_t)dout[k]);
+    if (rc) return rc;
+  }
+  EncodeParams& E = c->enc;
+  E.D_in = s->D_in; E.H1 = s->H1; E.offset = s->encode_offset;
+  E.cast32 = (nl == 6 || c->multinet) ? 1 : (s->label_fp32_cast != 0);
+  E.act = c->legacy ? kActLeaky : kActSigmoid;
+  const int label_par[5] = {PAYNE_P_TEFF, PAYNE_P_LOGG, PAYNE_P_FEH, PAYNE_P_AFE, PAYNE_P_VMIC};
+  for (int i = 0; i < 8; ++i) {
+    E.col[i] = -1; E.fixed[i] = std::numeric_limits<double>::quiet_NaN(); E.xmin[i] = 0; E.xmax[i] = 1;
+  }
+  for (int i = 0; i < s->D_in; ++i) {
+    E.xmin[i] = s->xmin[i]; E.xmax[i] = s->xmax[i];
+    if (i < 5) { E.col[i] = c->lay.col[label_par[i]]; E.fixed[i] = c->lay.fixed[label_par[i]]; }
+  }
+
+  int rc = PAYNE_OK;
+  if (!emulator_only) {
+    rc = build_tail(c, s, obs);
+    if (rc) return rc;
   }
   // Parity mode's "the tensor core never rounds the leading product sum" holds for contractions up to
   // 512 wide (mlp_tc.cuh header); wider hidden layers must use the CUDA-core fp32 mode.
@@ -639,7 +629,7 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
         E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
         (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb, rpg * c->actA.ld);
     c->launches++;
-    int rc = tc_run_multinet(c->tcw, c->b, H, c->D_out, G, P, &c->actA, &c->actB, rpg, nb, out, ldo,
+    int rc = tc_run_multinet_x(c->tcw, c->b, H, c->D_out, G, P, &c->actA, &c->actB, rpg, nb, out, ldo,
                              want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches,
                              out == c->flux ? rpg : 0);
     if (rc) return fail(rc, "tensor-core multi-chunk path failed");
@@ -679,7 +669,7 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
       c->launches++;
     }
   } else {
-    int rc = tc_run_layers(c->tcw, c->b, c->dims_in, c->dims_out, fused_split ? nullptr : c->hA, &c->actA, &c->actB,
+    int rc = tc_run_layers_x(c->tcw, c->b, c->dims_in, c->dims_out, fused_split ? nullptr : c->hA, &c->actA, &c->actB,
                            nb, out, ldo,
                            want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches, c->mapc,
                            out == c->flux ? c->actA.rows : 0);
@@ -709,7 +699,7 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       CU_TRY(cudaEventRecord(evs[0], st));
     }
     int is_depth = 0;
-    const bool fast_tail = c->has_spec && c->use_fast && c->allow_fast;
+    const bool fast_tail = c->has_spec && c->use_fast && c->allow_fast && !c->lsf_on;
     TailParams T = c->tail;
     if (c->has_spec) {
       T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb;
@@ -721,12 +711,28 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         // per-point setup depends only on theta: fork it beside the emulator GEMMs, join before the tail
         CU_TRY(cudaEventRecord(c->ev_fork, st));
         CU_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-        tail_setup_kernel<<<(nb + 63) / 64, 64, 0, c->side>>>(T, c->fast);
+        if (payne::launch_tail_setup(nb, c->side, T, c->fast)) return fail(PAYNE_E_CUDA, "tail_setup launch");
         CU_TRY(cudaEventRecord(c->ev_join, c->side));
         c->launches++;
       }
       rc = run_mlp(c, c->enc, th, ld, nb, c->flux, c->ldf, true, &is_depth, st);
       if (rc) return rc;
+      if (c->cont) {
+        // modspec *= np.interp(modwave, modcontwave, normalised F_lambda continuum) (predictspec.py:208-226)
+        PayneCtx* cc = c->cont;
+        cc->slab = c->slab; cc->lay.precision = c->lay.precision;
+        rc = ensure_workspace(cc, nb);
+        if (rc) return rc;
+        int cdepth = 0;
+        const long long l0 = cc->launches;
+        rc = run_mlp(cc, cc->enc, th, ld, nb, cc->flux, cc->ldf, false, &cdepth, st);
+        if (rc) return rc;
+        if (!is_depth) return fail(PAYNE_E_UNSUPPORTED, "continuum multiply expects line-depth rows");
+        ContParams C = c->contp;
+        C.cont = cc->flux; C.ldc = cc->ldf; C.flux = c->flux; C.ldf = c->ldf; C.B = nb;
+        if (payne::launch_continuum(std::min(nb, 8 * c->sm_count), st, C)) return fail(PAYNE_E_CUDA, "continuum launch");
+        c->launches += cc->launches - l0 + 1;
+      }
     }
     if (c->timing) CU_TRY(cudaEventRecord(evs[1], st));
     if (c->has_phot) {
@@ -740,28 +746,18 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
     if (c->has_spec) {
       T.flux_is_depth = is_depth;
       if (fast_tail) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
-      if (fast_tail && is_depth) {
+      if (c->lsf_on) {
+        TailParams TL = T;
+        TL.col[PAYNE_P_INSTR] = -1;                                   // the vector replaces Inst_R
+        TL.fixed[PAYNE_P_INSTR] = std::numeric_limits<double>::quiet_NaN();
+        if (payne::launch_tail_lsf(std::min(c->lsf_grid, nb), c->lsf_smem, st, TL, c->lsf)) return fail(PAYNE_E_CUDA, "tail launch");
+      } else if (fast_tail && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
-        switch (T.log2N1) {
-          case 10: tail_fast_kernel<10><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          case 11: tail_fast_kernel<11><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          case 12: tail_fast_kernel<12><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          case 13: tail_fast_kernel<13><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          case 14: tail_fast_kernel<14><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          case 15: tail_fast_kernel<15><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-          default: tail_fast_kernel<16><<<grid, kNT, c->fast_smem, st>>>(T, c->fast); break;
-        }
+        if (payne::launch_tail_fast(T.log2N1, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
       } else {
         if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
         const int grid = std::min(c->tail_grid, nb);
-        switch (T.log2N1 < 10 ? 10 : T.log2N1) {
-          case 10: tail_general_kernel<10><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-          case 11: tail_general_kernel<11><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-          case 12: tail_general_kernel<12><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-          case 13: tail_general_kernel<13><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-          case 14: tail_general_kernel<14><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-          default: tail_general_kernel<15><<<grid, kTailThreads, c->tail_smem, st>>>(T, c->fast.twc); break;
-        }
+        if (payne::launch_tail_general(T.log2N1, grid, c->tail_smem, st, T, c->fast.twc)) return fail(PAYNE_E_CUDA, "tail launch");
       }
       c->launches++;
     } else if (lnl) {
@@ -818,6 +814,7 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
 
 void payne_ctx_destroy(PayneCtx* c) {
   if (!c) return;
+  if (c->cont) { payne_ctx_destroy(c->cont); c->cont = nullptr; }
   DeviceGuard dg(c->device);
   cudaDeviceSynchronize();
   for (void* p : c->owned) cudaFree(p);
@@ -910,6 +907,81 @@ int payne_ann_eval(PayneCtx* c, const double* x_dev, int64_t B, float* y_dev, in
   return mark_done(c, (cudaStream_t)stream);
 }
 
+int payne_ctx_attach_continuum(PayneCtx* c, const PayneSpecNet* cnet) {
+  using namespace payne;
+  if (!c || !cnet) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
+  if (cnet->D_out < 2) return fail(PAYNE_E_INVALID, "continuum emulator needs at least two pixels");
+  DeviceGuard dg(c->device);
+  CU_TRY(cudaDeviceSynchronize());
+  if (c->cont) { payne_ctx_destroy(c->cont); c->cont = nullptr; }
+  PayneCtx* cc = new PayneCtx();
+  cc->device = c->device; cc->sm_count = c->sm_count; cc->lay = c->lay;
+  cc->has_spec = true; cc->has_phot = false;
+  cc->slab = c->slab;
+  int rc = PAYNE_OK;
+  if (cudaMalloc((void**)&cc->status, sizeof(int)) != cudaSuccess) rc = fail(PAYNE_E_NOMEM, "status");
+  if (!rc) rc = build_spec(cc, cnet, nullptr, /*emulator_only=*/true);
+  const int nc = cnet->D_out, n = c->D_out;
+  cc->ldf = ((long long)nc + 3) / 4 * 4;
+  std::vector<double> wc(cnet->wavelength, cnet->wavelength + nc), fac(nc);
+  for (int j = 0; j + 1 < nc && !rc; ++j)
+    if (!(wc[j + 1] > wc[j])) rc = fail(PAYNE_E_INVALID, "continuum wavelength grid must be strictly increasing");
+  // F_nu -> F_lambda factor, speedoflight / (wave * 1e-8)**2 (predictspec.py:219)
+  for (int j = 0; j < nc; ++j) { const double x = wc[j] * 1E-8; fac[j] = kSpeedOfLight / (x * x); }
+  // np.interp bracket of every emulator pixel in the continuum grid, -1 outside (left = right = nan)
+  std::vector<double> w(n);
+  std::vector<int> br(n, -1);
+  if (!rc) {
+    CU_TRY(cudaMemcpy(w.data(), c->tail.w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      if (w[i] < wc[0] || w[i] > wc[nc - 1] || w[i] != w[i]) continue;
+      int j = (int)(std::upper_bound(wc.begin(), wc.end(), w[i]) - wc.begin()) - 1;
+      br[i] = std::min(std::max(j, 0), nc - 1);
+    }
+  }
+  double *dfac = nullptr, *dwc = nullptr;
+  int* dbr = nullptr;
+  if (!rc) rc = upload_owned(cc, &dfac, fac.data(), nc);
+  if (!rc) rc = upload_owned(cc, &dwc, wc.data(), nc);
+  if (!rc) rc = upload_owned(cc, &dbr, br.data(), n);
+  if (rc) { std::string keep = g_err; payne_ctx_destroy(cc); g_err = keep; return rc; }
+  ContParams& C = c->contp;
+  C.n_c = nc; C.fac = dfac; C.wc = dwc; C.n = n; C.w = c->tail.w; C.bracket = dbr;
+  c->cont = cc;
+  c->tail.rows_may_nan = 1;          // pixels outside the continuum coverage are NaN from here on
+  return PAYNE_OK;
+}
+
+int payne_ctx_set_lsf(PayneCtx* c, const double* lsf_host, int64_t n) {
+  using namespace payne;
+  if (!c) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->has_spec) return fail(PAYNE_E_INVALID, "context has no spectrum emulator");
+  DeviceGuard dg(c->device);
+  CU_TRY(cudaDeviceSynchronize());
+  if (!lsf_host) { c->lsf_on = false; return PAYNE_OK; }
+  if (n != c->tail.n_obs) return fail(PAYNE_E_INVALID, "the LSF vector must have one dispersion per observed pixel");
+  if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "LSF broadening is limited to emulator grids of 32768 pixels");
+  for (int64_t j = 0; j < n; ++j)
+    if (!(lsf_host[j] > 0.0)) return fail(PAYNE_E_INVALID, "LSF dispersions must be positive");
+  if (!c->lsf.lsf) {
+    LsfParams& L = c->lsf;
+    L.log2nx_max = std::min(15, c->tail.log2tw);
+    const size_t smem = (size_t)4 << std::max(L.log2nx_max, c->tail.log2N1);
+    int occ = 0;
+    if (!payne::probe_tail_lsf(smem, &occ) || occ < 1) return fail(PAYNE_E_UNSUPPORTED, "LSF tail kernel does not fit on an SM");
+    c->lsf_smem = smem; c->lsf_grid = occ * c->sm_count;
+    double* d = nullptr;
+    CU_TRY(cudaMalloc((void**)&d, (size_t)n * sizeof(double))); c->owned.push_back(d); L.lsf = d;
+    CU_TRY(cudaMalloc((void**)&d, (size_t)c->lsf_grid * c->D_out * sizeof(double))); c->owned.push_back(d); L.cdf = d;
+    CU_TRY(cudaMalloc((void**)&d, (size_t)c->lsf_grid * c->D_out * sizeof(double))); c->owned.push_back(d); L.aux = d;
+    CU_TRY(cudaMalloc((void**)&d, ((size_t)c->lsf_grid << L.log2nx_max) * sizeof(double))); c->owned.push_back(d); L.lam = d;
+  }
+  CU_TRY(cudaMemcpy((void*)c->lsf.lsf, lsf_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  c->lsf_on = true;
+  return PAYNE_OK;
+}
+
 int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (!c || !key) return -1;
   std::string k(key);
@@ -925,6 +997,8 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "gauss_stencil") return c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
   if (k == "rot_window_floats") return c->fast.win_floats;
   if (k == "precision") return c->lay.precision;
+  if (k == "continuum") return c->cont != nullptr;
+  if (k == "lsf") return c->lsf_on;
   if (k == "status") {
     int v = 0;
     DeviceGuard dg(c->device);
@@ -960,6 +1034,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)
   if (k == "gauss_stencil") { c->tail.gauss_stencil = value != 0; return PAYNE_OK; }
+  if (k == "rows_may_nan") { c->tail.rows_may_nan = value != 0; return PAYNE_OK; }
   if (k == "inst_r_is_sigma") { c->tail.inst_scale = value ? 1.0 : payne::kFwhmFit; return PAYNE_OK; }   // profiling aid, see tail.cuh
   return fail(PAYNE_E_INVALID, "unknown key " + k);
 }
@@ -984,19 +1059,7 @@ int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_
   if (!rc) {
     cudaMemcpy(dA, A_host, (size_t)M * K * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(db, bias_host, (size_t)N * 4, cudaMemcpyHostToDevice);
-    const unsigned blocks = (unsigned)(((long long)M * K + 255) / 256);
-    if (precision == PAYNE_PREC_PARITY) {
-      x3_split_kernel<<<blocks, 256>>>(dA, K, (__nv_bfloat16*)a.plane[0], (__nv_bfloat16*)a.plane[1],
-                                       (__nv_bfloat16*)a.plane[2], a.ld, M, K);
-      rc = tc_launch<128, kModeX3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
-    } else {
-      tf32_split_kernel<<<blocks, 256>>>(dA, K, (float*)a.plane[0], (float*)a.plane[1], a.ld, M, K);
-      if (precision == PAYNE_PREC_3XTF32)
-        rc = tc_launch<128, kModeT3, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
-      else if (precision == PAYNE_PREC_TF32)
-        rc = tc_launch<128, kModeT1, 0>(a, K, w, db, dC, nullptr, nullptr, N, 0.f, M, prop.multiProcessorCount, 0);
-      else rc = PAYNE_E_UNSUPPORTED;
-    }
+    rc = tc_gemm_test_x(dA, M, N, K, precision, a, w, db, dC, prop.multiProcessorCount);
     if (rc) fail(rc, "gemm_test launch failed");
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(PAYNE_E_CUDA, cudaGetErrorString(cudaGetLastError()));
     if (!rc) cudaMemcpy(C_host, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);

@@ -76,6 +76,7 @@ struct TailParams {
   int B;
   int gauss_stencil;        // fast tail: instrumental broadening as a real-space stencil when the kernel is compact
   double inst_scale;        // Inst_R -> sigma-resolution: 2.355 (genmod.py:83, FWHM given) or 1 (getspec callers)
+  int rows_may_nan;         // rows can hold NaN although the labels are finite (continuum emulator attached)
   int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
                             // bit3 the regrid back, bit4 the final pass; results are garbage
 };
@@ -176,12 +177,12 @@ __device__ __forceinline__ float depth_of(float v, bool is_depth, bool fill_nan)
   return is_depth ? v : v - 1.f;
 }
 
-__device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S) {
+static __device__ void tail_setup(const TailParams& P, const double* th, PointSetup& S) {
   const double vrot = get_par(P, th, PAYNE_P_VROT);
   const double vrad = get_par(P, th, PAYNE_P_VRAD);
   const double instR = get_par(P, th, PAYNE_P_INSTR);
   S.bad = 0;
-  S.clean = 1;
+  S.clean = P.rows_may_nan ? 0 : 1;
   for (int i = 0; i < P.n_labels; ++i) {
     const double v = P.label_col[i] >= 0 ? th[P.label_col[i]] : P.label_fixed[i];
     if (!isfinite(v)) S.clean = 0;

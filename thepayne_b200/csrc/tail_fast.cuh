@@ -384,7 +384,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
 
 // One thread per point: mask limits, transform sizes, Doppler factor, taper constant, and the
 // stage-2 / final regrid ratios (the serial prologue of the tail, done for the whole slab at once).
-__global__ void __launch_bounds__(64)
+static __global__ void __launch_bounds__(64)
 tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.B) return;
@@ -405,7 +405,7 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
     // must fit the shared-memory transform buffer (no split transforms) and fill whole chunks
     const double spx = sqrt(S.sig_px2);
     const int R = (int)ceil(kStSigmas * spx);
-    if (P.gauss_stencil && spx >= kStMinSigmaPx && R <= kStMaxR && S.log2N2 >= 11 && S.log2N2 <= 15 &&
+    if (P.gauss_stencil && !P.rows_may_nan && spx >= kStMinSigmaPx && R <= kStMaxR && S.log2N2 >= 11 && S.log2N2 <= 15 &&
         F.win_floats >= kStSideFloats) {
       const int E = (R + 2) / 2;                       // offsets 2e-1, 2e, 2e+1 must cover [-R, R]
       FS.st_R = R;

@@ -34,6 +34,40 @@ def _pd(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def _specnet_struct(spec, keep):
+    """PayneSpecNet (include/payne_b200.h) for a ``synth.SpecNet``-like container; the numpy buffers the
+    struct points into are appended to ``keep``."""
+    sp = _lib.PayneSpecNet()
+    W = [_f32(w) for w in spec.weights]
+    b = [_f32(v) for v in spec.biases]
+    keep += W + b
+    nl = len(W)
+    nntype = getattr(spec, 'nntype', 'LinNet')
+    if (nl, nntype) not in [(6, 'LinNet'), (4, 'SMLP'), (3, 'YST1'), (4, 'MultiNet')]:
+        raise ValueError('unsupported emulator: %d layers of type %s' % (nl, nntype))
+    sp.D_in, sp.H1, sp.D_out = W[0].shape[-1], W[0].shape[-2], W[-1].shape[0]
+    if nntype == 'MultiNet':   # trainspec_multi.py:29-36, chunk nets stacked along axis 0
+        sp.H2 = sp.H3 = sp.H1
+        sp.n_groups, sp.group_size = int(W[0].shape[0]), int(spec.chunk)
+    elif nl == 6:        # NNmodels.py:147-152
+        sp.H2, sp.H3 = W[3].shape[0], W[4].shape[0]
+    elif nl == 4:        # NNmodels.py:99-107
+        sp.H2, sp.H3 = W[1].shape[0], W[2].shape[0]
+    else:                # ystpred.py:25-30
+        sp.H2, sp.H3 = W[1].shape[0], 0
+    sp.n_layers = nl
+    sp.activation = 0 if nntype in ('LinNet', 'MultiNet') else 1
+    sp.label_fp32_cast = 0 if nntype == 'YST1' else 1      # ystpred.py:47-50 stays in float64
+    for k in range(nl):
+        sp.W[k], sp.b[k] = _pf(W[k]), _pf(b[k])
+    xmin, xmax, wave = _f64(spec.xmin), _f64(spec.xmax), _f64(spec.wavelength)
+    keep += [xmin, xmax, wave]
+    sp.xmin, sp.xmax, sp.wavelength = _pd(xmin), _pd(xmax), _pd(wave)
+    sp.resolution = float(spec.resolution)
+    sp.encode_offset = float(getattr(spec, 'encode_offset', 0.5))
+    return sp
+
+
 class Engine:
     def __init__(self, spec=None, phot=None, obs_wave=None, obs_flux=None, obs_eflux=None,
                  obs_phot=None, fitpars_i=(), fixedpars=None, runbools=(True, False, False, False, False),
@@ -67,34 +101,7 @@ class Engine:
         if spec_bool:
             if spec is None:
                 raise ValueError('spec_bool set but no spectrum emulator given')
-            sp = _lib.PayneSpecNet()
-            W = [_f32(w) for w in spec.weights]
-            b = [_f32(v) for v in spec.biases]
-            keep += W + b
-            nl = len(W)
-            nntype = getattr(spec, 'nntype', 'LinNet')
-            if (nl, nntype) not in [(6, 'LinNet'), (4, 'SMLP'), (3, 'YST1'), (4, 'MultiNet')]:
-                raise ValueError('unsupported emulator: %d layers of type %s' % (nl, nntype))
-            sp.D_in, sp.H1, sp.D_out = W[0].shape[-1], W[0].shape[-2], W[-1].shape[0]
-            if nntype == 'MultiNet':   # trainspec_multi.py:29-36, chunk nets stacked along axis 0
-                sp.H2 = sp.H3 = sp.H1
-                sp.n_groups, sp.group_size = int(W[0].shape[0]), int(spec.chunk)
-            elif nl == 6:        # NNmodels.py:147-152
-                sp.H2, sp.H3 = W[3].shape[0], W[4].shape[0]
-            elif nl == 4:        # NNmodels.py:99-107
-                sp.H2, sp.H3 = W[1].shape[0], W[2].shape[0]
-            else:                # ystpred.py:25-30
-                sp.H2, sp.H3 = W[1].shape[0], 0
-            sp.n_layers = nl
-            sp.activation = 0 if nntype in ('LinNet', 'MultiNet') else 1
-            sp.label_fp32_cast = 0 if nntype == 'YST1' else 1      # ystpred.py:47-50 stays in float64
-            for k in range(nl):
-                sp.W[k], sp.b[k] = _pf(W[k]), _pf(b[k])
-            xmin, xmax, wave = _f64(spec.xmin), _f64(spec.xmax), _f64(spec.wavelength)
-            keep += [xmin, xmax, wave]
-            sp.xmin, sp.xmax, sp.wavelength = _pd(xmin), _pd(xmax), _pd(wave)
-            sp.resolution = float(spec.resolution)
-            sp.encode_offset = float(getattr(spec, 'encode_offset', 0.5))
+            sp = _specnet_struct(spec, keep)
             self.D_in, self.D_out = int(sp.D_in), int(sp.D_out)
         ob = _lib.PayneObs()
         self.n_obs = 0
@@ -152,6 +159,25 @@ class Engine:
         if key == 'precision' and isinstance(value, str):
             value = PREC[value]
         _lib.check(self.lib.payne_ctx_set(self._ctx, key.encode(), int(value)))
+
+    def attach_continuum(self, cont):
+        """Continuum emulator of ``PayneSpecPredict(Cnnpath=...)`` (predictspec.py:96-102): every model
+        spectrum is multiplied by the normalised F_lambda continuum interpolated onto the emulator grid
+        (predictspec.py:208-226)."""
+        keep = []
+        sp = _specnet_struct(cont, keep)
+        _lib.check(self.lib.payne_ctx_attach_continuum(self._ctx, C.byref(sp)))
+
+    def set_lsf(self, lsf):
+        """LSF vector: the dispersion (AA) at every observed pixel (predictspec.py:265-286); None switches
+        back to the scalar ``Inst_R`` stage."""
+        if lsf is None:
+            _lib.check(self.lib.payne_ctx_set_lsf(self._ctx, None, 0))
+            return
+        v = _f64(lsf)
+        if v.ndim != 1 or len(v) != self.n_obs:
+            raise ValueError('the LSF vector needs one dispersion per observed pixel (%d)' % self.n_obs)
+        _lib.check(self.lib.payne_ctx_set_lsf(self._ctx, v.ctypes.data, len(v)))
 
     def last_ms(self, which):
         return float(self.lib.payne_ctx_last_ms(self._ctx, {'mlp': 0, 'tail': 1, 'phot': 2}[which]))

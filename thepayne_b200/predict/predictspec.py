@@ -41,14 +41,18 @@ class ANN(object):
         self.wavelength = self.model.wavelength
         self.resolution = np.array(self.model.resolution, dtype=float)
         self.precision = kwargs.get('precision', 'parity')
+        self.continuum = None         # SpecNet of PayneSpecPredict's Cnnpath; attached to every engine made here
         self._engines = {}
 
-    def engine_for(self, outwave=None, npoly=0, inst_sigma=False):
+    def engine_for(self, outwave=None, npoly=0, inst_sigma=False, lsf=None):
         """Engine whose observed grid is ``outwave`` (None -> the emulator's own grid).
         ``inst_sigma``: the Inst_R column is the sigma-resolution ``getspec`` takes (predictspec.py:255-263),
-        not the FWHM resolution ``GenMod.genspec`` multiplies by 2.355 (genmod.py:82-85)."""
+        not the FWHM resolution ``GenMod.genspec`` multiplies by 2.355 (genmod.py:82-85).
+        ``lsf``: dispersion (AA) per pixel of ``outwave`` -- the LSF-vector form of ``inst_R``
+        (predictspec.py:265-286)."""
         ow = self.wavelength if outwave is None else np.ascontiguousarray(outwave, dtype=np.float64)
-        key = (ow.tobytes(), npoly, bool(inst_sigma))
+        lsf = None if lsf is None else np.ascontiguousarray(lsf, dtype=np.float64)
+        key = (ow.tobytes(), npoly, bool(inst_sigma), None if lsf is None else lsf.tobytes())
         if key not in self._engines:
             if len(self._engines) > 8:
                 self._engines.pop(next(iter(self._engines))).close()
@@ -59,6 +63,10 @@ class ANN(object):
                                         precision=self.precision)
             if inst_sigma:
                 self._engines[key].set('inst_r_is_sigma', 1)
+            if self.continuum is not None:
+                self._engines[key].attach_continuum(self.continuum)
+            if lsf is not None:
+                self._engines[key].set_lsf(lsf)
         return self._engines[key]
 
     def eval(self, x):
@@ -77,15 +85,23 @@ class PayneSpecPredict(object):
         self.NN = {}
         self.nnpath = nnpath
         self.NNtype = kwargs.get('NNtype', 'LinNet')
-        self.Cnnpath = kwargs.get('Cnnpath', None)
-        if self.Cnnpath is not None:
-            raise NotImplementedError('continuum ANN (Cnnpath) is outside the accelerated path')
+        self.C_NNtype = kwargs.get('C_NNtype', 'LinNet')
         self.anns = ANN(nnpath=nnpath, NNtype=self.NNtype, testing=False, verbose=False,
                         precision=kwargs.get('precision', 'parity'))
-        self.Canns = None
+        self.Cnnpath = kwargs.get('Cnnpath', None)
+        if self.Cnnpath is not None:          # predictspec.py:96-102
+            self.Canns = ANN(nnpath=self.Cnnpath, NNtype=self.C_NNtype, testing=False, verbose=False,
+                             precision=kwargs.get('precision', 'parity'))
+            self.anns.continuum = self.Canns.model
+        else:
+            self.Canns = None
 
     def predictspec(self, labels):
         return self.anns.eval(labels)
+
+    def predictcont(self, labels):
+        """predictspec.py:122-134."""
+        return self.Canns.eval(labels)
 
     def _labels(self, kwargs):
         """Keyword aliases of predictspec.py:154-198."""
@@ -104,31 +120,37 @@ class PayneSpecPredict(object):
         return d
 
     def getspec(self, **kwargs):
-        """Model spectrum for one label set (predictspec.py:136-294); scalar ``inst_R`` only."""
+        """Model spectrum for one label set (predictspec.py:136-294).  ``inst_R``: a float (sigma-resolution)
+        or a vector of dispersions in AA, one per pixel of ``outwave`` (of the native grid when ``outwave`` is
+        None) -- the LSF case of predictspec.py:265-286."""
         self.inputdict = self._labels(kwargs)
         outwave = kwargs.get('outwave', None)
         rot = kwargs.get('rot_vel', 0.0)
         rad = kwargs.get('rad_vel', 0.0)
         inst = kwargs.get('inst_R', np.nan)
-        if not isinstance(inst, float):
-            raise NotImplementedError('LSF-vector inst_R is outside the accelerated path')
+        lsf = None
+        if 'inst_R' in kwargs and not isinstance(inst, float):     # predictspec.py:255, 265
+            lsf = np.asarray(inst, dtype=np.float64)
         modwave = self.anns.wavelength
         if outwave is None:
             # no resampling of the wavelength axis: the reference returns the (shifted) native grid
             grid = modwave * (1.0 + (rad / speedoflight)) if rad != 0.0 else modwave
-            eng = self.anns.engine_for(grid, inst_sigma=True)
         else:
             outwave = np.array(outwave)
             grid = outwave
-            eng = self.anns.engine_for(outwave, inst_sigma=True)
+        if lsf is not None and len(lsf) != len(grid):              # predictspec.py:276-281
+            print('Length of LSF vector not equal to input wavelength')
+            raise AssertionError
+        eng = self.anns.engine_for(grid, inst_sigma=True, lsf=lsf)
         d = self.inputdict
         row = np.array([[d['teff'], d['logg'], d['feh'], d['afe'], rad, rot, d['vmic'],
-                         inst if inst > 0.0 else np.nan]], dtype=np.float64)
+                         inst if (lsf is None and inst > 0.0) else np.nan]], dtype=np.float64)
         flux, _, _ = eng.model_batch(row, want_mags=False)
         return grid, flux[0].cpu().numpy()
 
-    def getspec_batch(self, labels, rot_vel, rad_vel, inst_R, outwave, vmic=None):
-        """Batched extension: arrays of length B -> flux [B, len(outwave)] (CUDA tensor)."""
+    def getspec_batch(self, labels, rot_vel, rad_vel, inst_R, outwave, vmic=None, lsf=None):
+        """Batched extension: arrays of length B -> flux [B, len(outwave)] (CUDA tensor).  ``lsf``: one
+        dispersion vector (AA per pixel of ``outwave``) shared by the batch; ``inst_R`` is then ignored."""
         labels = np.asarray(labels, dtype=np.float64)
         B = labels.shape[0]
         th = np.full((B, 8), np.nan)
@@ -136,6 +158,7 @@ class PayneSpecPredict(object):
         th[:, 4], th[:, 5] = rad_vel, rot_vel
         if vmic is not None:
             th[:, 6] = vmic
-        th[:, 7] = np.asarray(inst_R, dtype=np.float64)
-        flux, _, _ = self.anns.engine_for(outwave, inst_sigma=True).model_batch(th, want_mags=False)
+        if lsf is None:
+            th[:, 7] = np.asarray(inst_R, dtype=np.float64)
+        flux, _, _ = self.anns.engine_for(outwave, inst_sigma=True, lsf=lsf).model_batch(th, want_mags=False)
         return flux
