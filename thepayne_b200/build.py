@@ -20,10 +20,10 @@ _FFT = ['fft.cuh', 'fft_ct.cuh', 'tail.cuh']
 _FAST = _FFT + ['tail_fast.cuh', 'tail_stencil.cuh', 'tail_general.cuh']
 # translation unit -> the headers whose change alters its object code
 UNITS = {
-    'payne_b200.cu': _GEMM + _FAST + ['launchers.h', 'phot.cuh', 'continuum.cuh'],
-    'gemm_tu.cu': _GEMM + ['launchers.h'],
+    'payne_b200.cu': ['mlp_simt.cuh', 'mlp_tc_types.h'] + _FAST + ['launchers.h', 'phot.cuh', 'continuum.cuh', 'tail_lsf.cuh'],
+    'gemm_tu.cu': _GEMM + ['mlp_tc_types.h', 'launchers.h'],
     'tail_fast_tu.cu': _FAST + ['launchers.h'],
-    'tail_general_tu.cu': _FFT + ['tail_general.cuh', 'tail_lsf.cuh', 'launchers.h'],
+    'tail_general_tu.cu': _FFT + ['tail_general.cuh', 'tail_lsf.cuh', 'continuum.cuh', 'launchers.h'],
 }
 
 
@@ -39,8 +39,14 @@ def _deps(unit):
            [os.path.join(CSRC, h) for h in UNITS[unit] if os.path.exists(os.path.join(CSRC, h))]
 
 
+# Development switch: PAYNE_FAST_ONLY=14 compiles the fast tail for that transform size only (every other
+# size then reports "unsupported"); the object gets its own name so a full build never picks it up.
+FAST_ONLY = os.environ.get('PAYNE_FAST_ONLY', '')
+
+
 def _obj(unit):
-    return os.path.join(OBJ, unit[:-3] + '.o')
+    tag = ('_only' + FAST_ONLY) if (FAST_ONLY and unit == 'tail_fast_tu.cu') else ''
+    return os.path.join(OBJ, unit[:-3] + tag + '.o')
 
 
 def _stale(unit):
@@ -52,6 +58,8 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
+    if FAST_ONLY and (_stale('tail_fast_tu.cu') or os.path.getmtime(_obj('tail_fast_tu.cu')) > t):
+        return True
     return any(os.path.getmtime(d) > t for u in UNITS for d in _deps(u))
 
 
@@ -62,6 +70,8 @@ def _compile(unit, verbose):
            '-Xcompiler', '-fPIC', '-c', '-o', _obj(unit), os.path.join(CSRC, unit)]
     if verbose:
         cmd[1:1] = ['-Xptxas', '-v']
+    if FAST_ONLY and unit == 'tail_fast_tu.cu':
+        cmd[1:1] = ['-DPAYNE_FAST_ONLY=' + FAST_ONLY]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return unit, r
 

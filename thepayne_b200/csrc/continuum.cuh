@@ -98,7 +98,8 @@ __device__ double nanmedian_dev(const VF& val, int n, int* hist, unsigned long l
   return (a + b) / 2.0;                                  // np.mean of the two middle values
 }
 
-static __global__ void __launch_bounds__(256) continuum_kernel(const __grid_constant__ ContParams C) {
+template <int kUnused = 0>
+__global__ void __launch_bounds__(256) continuum_kernel(const __grid_constant__ ContParams C) {
   __shared__ int hist[256];
   __shared__ unsigned long long sh_prefix;
   __shared__ int sh_rank, sh_count;

@@ -1,7 +1,23 @@
 // Translation unit of the tcgen05 GEMM templates (mlp_tc.cuh); see launchers.h.
+#include "mlp_tc.cuh"
 #include "launchers.h"
 
 namespace payne {
+
+int tc_prepare_weights_x(TcWeights* w, const float* W_host, int N, int K, std::vector<void*>* owned) {
+  return tc_prepare_weights(w, W_host, N, K, owned);
+}
+int tc_alloc_acts_x(TcActs* a, long long rows, long long ld) { return tc_alloc_acts(a, rows, ld); }
+void tc_free_acts_x(TcActs* a) { tc_free_acts(a); }
+
+int launch_encode_x3(const EncodeParams& E, const double* x, long long ld, const float* W1, const float* b1,
+                     TcActs* acts, int nb, int grid_y, long long plane_gstride, cudaStream_t st) {
+  dim3 grid((unsigned)((nb + 7) / 8), (unsigned)grid_y);
+  encode_layer1_x3_kernel<<<grid, 256, 0, st>>>(E, x, ld, W1, b1, (__nv_bfloat16*)acts->plane[0],
+                                                (__nv_bfloat16*)acts->plane[1], (__nv_bfloat16*)acts->plane[2],
+                                                acts->ld, nb, plane_gstride);
+  return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
+}
 
 int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                     const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,

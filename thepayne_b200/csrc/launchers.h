@@ -4,13 +4,20 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "mlp_tc.cuh"
+#include "mlp_simt.cuh"
+#include "mlp_tc_types.h"
 #include "tail_fast.cuh"
 #include "tail_lsf.cuh"
 
 namespace payne {
 
 // ---- gemm_tu.cu: lin2..lin6 on tcgen05 (mlp_tc.cuh)
+int tc_prepare_weights_x(TcWeights* w, const float* W_host, int N, int K, std::vector<void*>* owned);
+int tc_alloc_acts_x(TcActs* a, long long rows, long long ld);
+void tc_free_acts_x(TcActs* a);
+// encode + lin1 + operand slicing (parity mode); grid_y = chunk nets (1 otherwise)
+int launch_encode_x3(const EncodeParams& E, const double* x, long long ld, const float* W1, const float* b1,
+                     TcActs* acts, int nb, int grid_y, long long plane_gstride, cudaStream_t st);
 int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                     const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
                     float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,

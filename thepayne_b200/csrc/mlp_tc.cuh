@@ -38,21 +38,11 @@
 
 #include "../../include/payne_b200.h"
 #include "mlp_simt.cuh"
+#include "mlp_tc_types.h"
 
 namespace payne {
 
 enum { kModeT1 = 0, kModeT3 = 1, kModeX3 = 2 };
-
-struct TcWeights {
-  void* plane[3] = {nullptr, nullptr, nullptr};   // T: fp32 hi, lo ; X3: bf16 q1, q2, q3
-  void* xplane[3] = {nullptr, nullptr, nullptr};
-  float* scale = nullptr;                          // X3: per-row power of two
-  int N = 0, K = 0, Kp = 0;                        // Kp: row pitch in elements (16-byte multiple for TMA)
-};
-struct TcActs {
-  void* plane[3] = {nullptr, nullptr, nullptr};    // sized for fp32; bf16 planes alias the storage
-  long long rows = 0, ld = 0;
-};
 
 // ------------------------------------------------------------------ PTX wrappers
 namespace ptx {
@@ -249,7 +239,6 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
 #define PAYNE_GEMM_2SM_DEFAULT 0
 #endif
 constexpr int kTcThreads = 256;
-constexpr int kX3MaxK = 512;    // widest contraction the exact-accumulation split covers (see header)
 // Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get four
 // groups of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and took more
 // than half of the kernel; each group takes 16 of the tile's 64 columns.
@@ -341,23 +330,6 @@ struct TcCfg {
   static constexpr int kAccCols = MODE == kModeX3 ? 2 * BN : BN;  // columns per accumulator set
   static constexpr int kTmemCols = 2 * kAccCols;                  // double buffered
   static_assert(kTmemCols <= 512, "TMEM budget");
-};
-
-struct TcMaps {
-  CUtensorMap a[3];
-  CUtensorMap b[3];
-  CUtensorMap c;       // EPI 0: fp32 output [M, N] (pitch ldc), boxes of 32 x 32, 128B swizzle
-};
-
-// Tensor maps of one layer, reusable while the buffers stay put: encoding seven descriptors through
-// the driver costs several microseconds of host time per launch, which is what bounds the latency
-// of small batches.  The maps cover `rows` (the allocated row count), not the batch: rows past the
-// batch are computed on stale data and land in workspace rows nobody reads.
-struct TcMapCache {
-  TcMaps maps;
-  const void* a0 = nullptr; const void* out = nullptr;
-  long long rows = 0, lda = 0, ldc = 0;
-  int variant = -1;
 };
 
 

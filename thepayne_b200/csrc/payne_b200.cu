@@ -508,19 +508,19 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs, bool emu
       return fail(PAYNE_E_UNSUPPORTED, "multi-chunk emulator: precision must be 'parity' or 'simt'");
     const int G = c->n_groups, H = s->H1;
     for (int k = 1; k <= 2; ++k) {
-      rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], G * H, H, &c->owned);
+      rc = payne::tc_prepare_weights_x(&c->tcw[k], s->W[k], G * H, H, &c->owned);
       if (rc) return fail(rc, "tc_prepare_weights failed");
     }
     // output layers padded to G * chunk rows so that every group's weight block has the same height
     std::vector<float> w4((size_t)G * c->chunk * H, 0.f);
     std::memcpy(w4.data(), s->W[3], (size_t)s->D_out * H * sizeof(float));
-    rc = payne::tc_prepare_weights(&c->tcw[3], w4.data(), G * c->chunk, H, &c->owned);
+    rc = payne::tc_prepare_weights_x(&c->tcw[3], w4.data(), G * c->chunk, H, &c->owned);
     if (rc) return fail(rc, "tc_prepare_weights failed");
     return PAYNE_OK;
   }
   // tensor-core operand copies of the weights (sigmoid LinNet only)
   for (int k = 1; k < 6 && !c->legacy; ++k) {
-    rc = payne::tc_prepare_weights(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
+    rc = payne::tc_prepare_weights_x(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
     if (rc) return fail(rc, "tc_prepare_weights failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
   }
   return PAYNE_OK;
@@ -567,7 +567,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
   auto drop = [&](void* p) { if (p) cudaFree(p); };
   drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
   c->fast.points = nullptr;
-  payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
+  payne::tc_free_acts_x(&c->actA); payne::tc_free_acts_x(&c->actB);
   c->flux = c->hA = c->hB = nullptr; c->chi2_sed = nullptr; c->slab_alloc = 0;
   const long long rows = (need + 127) / 128 * 128;
   if (c->has_spec) {
@@ -580,8 +580,8 @@ int ensure_workspace(PayneCtx* c, long long B) {
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)arows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
     CU_TRY(cudaMemset(c->fast.points, 0, (size_t)rows * sizeof(payne::FastPoint)));   // struct padding is copied too
-    int rc = payne::tc_alloc_acts(&c->actA, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
-    rc = payne::tc_alloc_acts(&c->actB, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+    int rc = payne::tc_alloc_acts_x(&c->actA, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
+    rc = payne::tc_alloc_acts_x(&c->actB, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
   }
   CU_TRY(cudaMalloc((void**)&c->chi2_sed, (size_t)rows * sizeof(double)));
   // the zero-fills above went to the NULL stream; callers may launch on non-blocking streams that do
@@ -624,10 +624,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
       CU_TRY(cudaGetLastError());
       return PAYNE_OK;
     }
-    dim3 ge((unsigned)((nb + 7) / 8), (unsigned)G);
-    encode_layer1_x3_kernel<<<ge, 256, 0, st>>>(
-        E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
-        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb, rpg * c->actA.ld);
+    if (launch_encode_x3(E, x, ld, c->W[0], c->b[0], &c->actA, nb, G, rpg * c->actA.ld, st))
+      return fail(PAYNE_E_CUDA, "encode launch");
     c->launches++;
     int rc = tc_run_multinet_x(c->tcw, c->b, H, c->D_out, G, P, &c->actA, &c->actB, rpg, nb, out, ldo,
                              want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches,
@@ -639,9 +637,7 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
   const bool simt = c->legacy || prec == PAYNE_PREC_SIMT_FP32;
   const bool fused_split = !simt && (prec == PAYNE_PREC_PARITY);   // encode + lin1 + slicing in one kernel
   if (fused_split) {
-    encode_layer1_x3_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(
-        E, x, ld, c->W[0], c->b[0], (__nv_bfloat16*)c->actA.plane[0], (__nv_bfloat16*)c->actA.plane[1],
-        (__nv_bfloat16*)c->actA.plane[2], c->actA.ld, nb, 0);
+    if (launch_encode_x3(E, x, ld, c->W[0], c->b[0], &c->actA, nb, 1, 0, st)) return fail(PAYNE_E_CUDA, "encode launch");
   } else {
     const long long tot = (long long)nb * c->H[0];
     encode_layer1_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(E, x, ld, c->W[0], c->b[0], c->hA,
@@ -821,7 +817,7 @@ void payne_ctx_destroy(PayneCtx* c) {
   auto drop = [&](void* p) { if (p) cudaFree(p); };
   drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
   c->fast.points = nullptr; drop(c->status);
-  payne::tc_free_acts(&c->actA); payne::tc_free_acts(&c->actB);
+  payne::tc_free_acts_x(&c->actA); payne::tc_free_acts_x(&c->actB);
   drop(c->theta_stage); drop(c->lnl_stage);
   if (c->theta_pin) cudaFreeHost(c->theta_pin);
   if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
@@ -1048,11 +1044,11 @@ int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   std::vector<void*> owned;
   TcWeights w;
-  int rc = tc_prepare_weights(&w, W_host, N, K, &owned);
+  int rc = tc_prepare_weights_x(&w, W_host, N, K, &owned);
   TcActs a;
   const long long rows = (M + 127) / 128 * 128, ld = (K + 7) / 8 * 8;
   float *dA = nullptr, *dC = nullptr, *db = nullptr;
-  if (!rc) rc = tc_alloc_acts(&a, rows, ld);
+  if (!rc) rc = tc_alloc_acts_x(&a, rows, ld);
   if (!rc && (cudaMalloc((void**)&dA, (size_t)M * K * 4) != cudaSuccess ||
               cudaMalloc((void**)&dC, (size_t)M * N * 4) != cudaSuccess ||
               cudaMalloc((void**)&db, (size_t)N * 4) != cudaSuccess)) rc = fail(PAYNE_E_NOMEM, "gemm_test alloc");
@@ -1064,7 +1060,7 @@ int payne_gemm_test(const float* A_host, const float* W_host, const float* bias_
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail(PAYNE_E_CUDA, cudaGetErrorString(cudaGetLastError()));
     if (!rc) cudaMemcpy(C_host, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
   }
-  tc_free_acts(&a);
+  tc_free_acts_x(&a);
   if (dA) cudaFree(dA); if (dC) cudaFree(dC); if (db) cudaFree(db);
   for (void* p : owned) cudaFree(p);
   return rc;

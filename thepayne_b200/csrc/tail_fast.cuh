@@ -384,7 +384,8 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
 
 // One thread per point: mask limits, transform sizes, Doppler factor, taper constant, and the
 // stage-2 / final regrid ratios (the serial prologue of the tail, done for the whole slab at once).
-static __global__ void __launch_bounds__(64)
+template <int kUnused = 0>
+__global__ void __launch_bounds__(64)
 tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.B) return;

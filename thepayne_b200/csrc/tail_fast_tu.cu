@@ -3,7 +3,12 @@
 
 namespace payne {
 
+// PAYNE_FAST_ONLY=<log2 N1> (development builds, thepayne_b200/build.py): compile that one transform size only
+#ifdef PAYNE_FAST_ONLY
+#define PAYNE_FAST_SIZES(X) X(PAYNE_FAST_ONLY)
+#else
 #define PAYNE_FAST_SIZES(X) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#endif
 
 bool probe_tail_fast(int l2, size_t bytes, int* occ) {
   cudaError_t e1 = cudaErrorInvalidValue, e2 = cudaErrorInvalidValue;
@@ -32,7 +37,7 @@ int launch_tail_fast(int l2, int grid, size_t smem, cudaStream_t st, const TailP
 }
 
 int launch_tail_setup(int nb, cudaStream_t st, const TailParams& T, const FastGrid& F) {
-  tail_setup_kernel<<<(nb + 63) / 64, 64, 0, st>>>(T, F);
+  tail_setup_kernel<0><<<(nb + 63) / 64, 64, 0, st>>>(T, F);
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 

@@ -33,8 +33,8 @@ int launch_tail_general(int l2, int grid, size_t smem, cudaStream_t st, const Ta
 }
 
 bool probe_tail_lsf(size_t bytes, int* occ) {
-  if (cudaFuncSetAttribute(tail_lsf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, tail_lsf_kernel, kTailThreads, bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(tail_lsf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, tail_lsf_kernel<0>, kTailThreads, bytes) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
@@ -42,12 +42,12 @@ bool probe_tail_lsf(size_t bytes, int* occ) {
 }
 
 int launch_tail_lsf(int grid, size_t smem, cudaStream_t st, const TailParams& T, const LsfParams& L) {
-  tail_lsf_kernel<<<grid, kTailThreads, smem, st>>>(T, L);
+  tail_lsf_kernel<0><<<grid, kTailThreads, smem, st>>>(T, L);
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
 int launch_continuum(int grid, cudaStream_t st, const ContParams& C) {
-  continuum_kernel<<<grid, 256, 0, st>>>(C);
+  continuum_kernel<0><<<grid, 256, 0, st>>>(C);
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 

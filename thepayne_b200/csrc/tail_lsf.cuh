@@ -62,7 +62,8 @@ __device__ __forceinline__ double np_interp(double x, const XF& xp, const FF& fp
   return r;
 }
 
-static __global__ void __launch_bounds__(kTailThreads, 1)
+template <int kUnused = 0>
+__global__ void __launch_bounds__(kTailThreads, 1)
 tail_lsf_kernel(const __grid_constant__ TailParams P, const __grid_constant__ LsfParams L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);
