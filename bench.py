@@ -452,6 +452,30 @@ def run_ours(args):
     except Exception:
         pass
     tail_gbs = tail_bytes / (tail_ms * 1e-3) / 1e9
+    # the two on-chip rooflines the tail actually runs against: shared-memory wavefronts
+    # (128 B per clock per SM) and warp-instruction issue (4 per clock per SM), per-point counts from the
+    # committed ncu census, live time and live SM clock
+    smem_roof = issue_roof = None
+    try:
+        cen = tfile['tail_census']
+        clk = (sampler.summary().get('sm_mhz') or sampler.summary().get('sm_max_mhz') or 1965.0) * 1e6
+        sms = eng.query('sm_count')
+        wf, wfi, wi = cen['smem_wavefronts_per_point'], cen['smem_wavefronts_ideal_per_point'], cen['warp_instructions_per_point']
+        a = wfi * 128.0 * B / (tail_ms * 1e-3) / 1e9
+        pk = sms * 128.0 * clk / 1e9
+        smem_roof = {'kernel': 'tail_fast_kernel', 'bound': 'shared-memory', 'achieved': a, 'peak': pk, 'unit': 'GB/s',
+                     'frac': a / pk, 'frac_with_conflict_replays': wf * 128.0 * B / (tail_ms * 1e-3) / 1e9 / pk,
+                     'wavefronts_per_point': wf, 'ideal_wavefronts_per_point': wfi,
+                     'note': 'conflict-free wavefronts x 128 B per point x points / live tail time, against SMs x 128 B/clk x '
+                             'live SM clock; counts from ' + cen['source']}
+        ai = wi * B / (tail_ms * 1e-3) / 1e9
+        pi = sms * 4.0 * clk / 1e9
+        issue_roof = {'kernel': 'tail_fast_kernel', 'bound': 'issue', 'achieved': ai, 'peak': pi, 'unit': 'G warp-inst/s',
+                      'frac': ai / pi, 'warp_instructions_per_point': wi,
+                      'note': 'executed warp instructions per point x points / live tail time, against SMs x 4 schedulers x '
+                              'live SM clock; the kernel is co-limited by issue and the shared-memory pipe (DESIGN.md 3.3)'}
+    except Exception:
+        pass
     fl = mlp_flops(cfg) * B
     mlp_tfs = fl / (mlp_ms * 1e-3) / 1e12
     res = {
@@ -473,6 +497,7 @@ def run_ours(args):
                      'note': 'algorithmic bytes = B*(4*D_out+4). The kernel cannot be HBM-bound under reference '
                              'semantics: 4 in-shared-memory FFTs of 16384 samples per point make the L1/shared-memory '
                              'data pipe the busiest unit (limiter, from the committed ncu capture); see DESIGN.md'},
+        'roofline_smem': smem_roof, 'roofline_issue': issue_roof,
         'roofline_mlp': {'kernel': 'tc_gemm_kernel x5 (+lin1)', 'bound': 'tensor', 'achieved': mlp_tfs,
                          'peak': tf_burst / 2, 'unit': 'TFLOP/s', 'frac': mlp_tfs / (tf_burst / 2),
                          'ms_per_step': mlp_ms,

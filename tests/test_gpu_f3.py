@@ -90,14 +90,25 @@ def test_continuum_lnl_path_and_vmic():
     assert eng.query('continuum') == 1
     flux, _, lnl = eng.model_batch(torch.from_numpy(th).cuda(), want_mags=False)
     flux, lnl = flux.cpu().numpy(), lnl.cpu().numpy()
-    net, cnet = O.make_net(cfg.spec), O.make_net(cont)
     ix = {p: i for i, p in enumerate(cfg.fitpars_i)}
-    for b in range(len(th)):
-        t = th[b]
-        _, fr = O.getspec(net, cfg.spec, t[ix['Teff']], t[ix['log(g)']], t[ix['[Fe/H]']], t[ix['[a/Fe]']], t[ix['Vmic']],
-                          t[ix['Vrot']], t[ix['Vrad']], 2.355 * t[ix['Inst_R']], cfg.obs_wave, cont=(cnet, cont))
-        fr = fr * O.polycalc([t[ix['pc_0']], t[ix['pc_1']]], cfg.obs_wave)
-        assert np.max(np.abs(flux[b] - fr) / np.abs(fr)) <= 5e-7
-        lr = -0.5 * np.sum(((fr - cfg.obs_flux) ** 2.0) / (cfg.obs_eflux ** 2.0))
-        assert abs(lnl[b] - lr) <= 1e-3, (lnl[b], lr)
+
+    def oracle(ideal):
+        net, cnet = O.make_net(cfg.spec, ideal=ideal), O.make_net(cont, ideal=ideal)
+        fl, ll = [], []
+        for t in th:
+            _, fr = O.getspec(net, cfg.spec, t[ix['Teff']], t[ix['log(g)']], t[ix['[Fe/H]']], t[ix['[a/Fe]']], t[ix['Vmic']],
+                              t[ix['Vrot']], t[ix['Vrad']], 2.355 * t[ix['Inst_R']], cfg.obs_wave, cont=(cnet, cont))
+            fr = fr * O.polycalc([t[ix['pc_0']], t[ix['pc_1']]], cfg.obs_wave)
+            fl.append(fr)
+            ll.append(-0.5 * np.sum(((fr - cfg.obs_flux) ** 2.0) / (cfg.obs_eflux ** 2.0)))
+        return np.array(fl), np.array(ll)
+    fr, lr = oracle(False)          # the reference's arithmetic: both emulators in torch float32
+    fi, li = oracle(True)           # both emulators in float64
+    assert np.max(np.abs(flux - fr) / np.abs(fr)) <= 5e-7
+    # The continuum net's float32 output (1 ulp = 6e-8 of a value near 1) is interpolated from a grid ~6x coarser
+    # than the observed one, so its rounding is coherent over several observed pixels and moves lnL by a few
+    # 1e-3 even at |lnL| ~ 1e4 -- in the reference just as here.  The bar is therefore the reference's own
+    # distance from exact arithmetic on these rows (never below the flat 1e-3).
+    floor = max(1e-3, 2.0 * float(np.max(np.abs(lr - li))))
+    assert np.all(np.abs(lnl - lr) <= floor) and np.all(np.abs(lnl - li) <= floor), (lnl - lr, lr - li)
     eng.close()

@@ -310,6 +310,22 @@ def test_differential_fuzz_against_the_oracle():
     assert gpu_fuzz.run(seed=1, ncfg=14, verbose=False) == 0
 
 
+@pytest.mark.parametrize('seed,cfgs', [(21, [31, 34]), (22, [35]), (25, [36])])
+def test_fuzz_far_points_sit_at_the_float32_noise_floor(seed, cfgs):
+    """The configurations of the second fuzz batch (seeds 21-25) whose far-off points (|lnL| 2.5e4..2.5e5,
+    continuum polynomial, emulator pixels oversampled up to 2.4x by the observed grid) differ from the
+    reference by more than 1e-3 (up to 5.3e-3 = 2.2e-8 relative).  With the emulator evaluated in float64 the
+    reference itself is 0.45e-3..3.2e-3 from exact arithmetic there.  The CUDA path must be at least as close as
+    the reference or within max(1e-3, 3e-8 |lnL|) of the exact value: profiles/r02_fuzz_diag.txt splits the worst
+    point (seed 25 / cfg 36, lnL -98750: CUDA 2.35e-3 from exact, reference 1.0e-3) into 2.4e-4 from the fp32
+    tail and the rest from the float32 rounding of the 16-wide hidden activations -- the noise floor of any fp32
+    emulator, with either sign on either side."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import gpu_fuzz
+    assert gpu_fuzz.run(seed=seed, ncfg=max(cfgs) + 1, verbose=False, only=cfgs) == 0
+
+
 def test_gauss_stencil_agrees_with_fft_stage():
     """Instrumental broadening as a real-space stencil (compact kernels) against the FFT convolution it
     replaces, on the same points: the two are the same circular convolution (tail_stencil.cuh)."""
@@ -318,7 +334,10 @@ def test_gauss_stencil_agrees_with_fft_stage():
         eng = _engine(cfg, 'parity')
         th = torch.from_numpy(np.ascontiguousarray(np.vstack([g['theta'], cfg.draw(64, seed=8)]))).cuda()
         eng.set('gauss_stencil', 1)                  # opt-in path (the FFT is the default: it is as fast)
-        assert eng.query('gauss_stencil') == 1, eng.query('rot_window_floats')
+        if eng.query('gauss_stencil') != 1:
+            eng.close()
+            pytest.skip('library built without -DPAYNE_WITH_STENCIL=1 (the default: the stencil is no faster than '
+                        'the FFT stage and its shared memory comes out of the rotation-table window)')
         fa, _, la = eng.model_batch(th)
         la2 = eng.lnlike_batch(th)
         eng.set('gauss_stencil', 0)

@@ -54,8 +54,18 @@ def _stale(unit):
     return not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in _deps(unit))
 
 
+FLAVOR = os.path.join(OBJ, 'flavor')      # which tail_fast object the current .so was linked from
+
+
+def _flavor():
+    try:
+        return open(FLAVOR).read().strip()
+    except OSError:
+        return '?'
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or _flavor() != ('only' + FAST_ONLY if FAST_ONLY else 'full'):
         return True
     t = os.path.getmtime(OUT)
     if FAST_ONLY and (_stale('tail_fast_tu.cu') or os.path.getmtime(_obj('tail_fast_tu.cu')) > t):
@@ -92,6 +102,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stderr[-4000:])
+    with open(FLAVOR, 'w') as f:
+        f.write('only' + FAST_ONLY if FAST_ONLY else 'full')
     return OUT
 
 

@@ -18,7 +18,8 @@
 namespace payne {
 
 struct ContParams {
-  const float* cont;        // [B, ldc] continuum net output (flux, not depth)
+  const float* cont;        // [B, ldc] continuum net output: c, or c - 1 when cont_is_depth (3 more mantissa bits)
+  int cont_is_depth;
   long long ldc;
   int n_c;
   const double* fac;        // [n_c] speedoflight / (wc * 1e-8)^2
@@ -108,18 +109,19 @@ __global__ void __launch_bounds__(256) continuum_kernel(const __grid_constant__ 
     const float* crow = C.cont + (long long)p * C.ldc;
     float* frow = C.flux + (long long)p * C.ldf;
     const float* cr = crow; const double* fac = C.fac;
-    const double med = nanmedian_dev([cr, fac](int j) { return (double)__ldg(cr + j) * __ldg(fac + j); }, C.n_c, hist,
+    const double off = C.cont_is_depth ? 1.0 : 0.0;
+    const double med = nanmedian_dev([cr, fac, off](int j) { return ((double)__ldg(cr + j) + off) * __ldg(fac + j); }, C.n_c, hist,
                                      &sh_prefix, &sh_rank, &sh_count);
     for (int i = tid; i < C.n; i += blockDim.x) {
       const int j = __ldg(C.bracket + i);
       double c = CUDART_NAN;
       if (j >= 0) {
         const double x = __ldg(C.w + i), x0 = __ldg(C.wc + j);
-        const double f0 = ((double)__ldg(crow + j) * __ldg(C.fac + j)) / med;
+        const double f0 = (((double)__ldg(crow + j) + off) * __ldg(C.fac + j)) / med;
         if (j == C.n_c - 1 || x == x0) c = f0;
         else {
           const double x1 = __ldg(C.wc + j + 1);
-          const double f1 = ((double)__ldg(crow + j + 1) * __ldg(C.fac + j + 1)) / med;
+          const double f1 = (((double)__ldg(crow + j + 1) + off) * __ldg(C.fac + j + 1)) / med;
           const double slope = (f1 - f0) / (x1 - x0);
           c = slope * (x - x0) + f0;
           if (c != c) {                                 // numpy's fallbacks for NaN / inf neighbours

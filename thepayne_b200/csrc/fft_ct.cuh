@@ -238,8 +238,9 @@ __device__ __forceinline__ void ct_fft_forward(float2* z, const TwTab& tw, const
 // position k * num / den (see tail_fast.cuh regrid_in, whose arithmetic this repeats).  Fusing the
 // regrid into the pass saves one full write + read of the transform buffer and a block barrier, and
 // lets the interpolation arithmetic run under the pass's shared-memory time.  The row must carry two
-// finite pad floats behind its last used element; NaN samples read as 0 (nan_to_num in depth space).
-template <int LOG2M>
+// finite pad floats behind its last used element; NaN samples read as 0 (nan_to_num in depth space) unless
+// CLEAN says the row cannot hold any (finite labels, no continuum emulator: 6 of ~40 instructions per pair).
+template <int LOG2M, bool CLEAN>
 __device__ __forceinline__ void ct_pass0_regrid(float2* z, const TwTab& tw, const TwConst& tc, int tid,
                                                 const float* __restrict__ row, int num, int den, float invden,
                                                 float c) {
@@ -280,9 +281,11 @@ __device__ __forceinline__ void ct_pass0_regrid(float2* z, const TwTab& tw, cons
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         float a0 = src[0], a1 = src[1], a2 = src[2];
-        if (a0 != a0) a0 = 0.f;
-        if (a1 != a1) a1 = 0.f;
-        if (a2 != a2) a2 = 0.f;
+        if (!CLEAN) {
+          if (a0 != a0) a0 = 0.f;
+          if (a1 != a1) a1 = 0.f;
+          if (a2 != a2) a2 = 0.f;
+        }
         const int rem1 = rr + num;
         const bool same = rem1 < den;              // second sample still between row[j] and row[j+1]
         const float lo = same ? a0 : a1, hi = same ? a1 : a2;
@@ -488,8 +491,10 @@ __device__ __forceinline__ void ct_convolve_split(float2* z, float2* g, const Tw
 // ct_convolve with the regrid of the input row fused into the first pass (see ct_pass0_regrid)
 template <int LOG2M, class HF>
 __device__ __forceinline__ void ct_convolve_regrid(float2* z, const TwTab& tw, const TwConst& tc, const HF& H, int tid,
-                                                   const float* row, int num, int den, float invden, float c) {
-  ct_pass0_regrid<LOG2M>(z, tw, tc, tid, row, num, den, invden, c);
+                                                   const float* row, int num, int den, float invden, float c,
+                                                   bool clean) {
+  if (clean) ct_pass0_regrid<LOG2M, true>(z, tw, tc, tid, row, num, den, invden, c);
+  else ct_pass0_regrid<LOG2M, false>(z, tw, tc, tid, row, num, den, invden, c);
   ct_fft_forward_rest<LOG2M>(z, tw, tc, tid);
   ct_filter_pairs<LOG2M>(z, tw, H, tid);
   ct_fft_inverse<LOG2M>(z, tw, tc, tid);

@@ -279,9 +279,18 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   const double vmax = 600.0;
   long long ntab = (long long)std::ceil(3.14159265358979323846 * vmax / dv1 / h) + 8;
   ntab = std::min<long long>(ntab, 1LL << 21);
-  std::vector<float> sbt(ntab + 3);
-  for (long long i = 0; i < ntab + 3; ++i) sbt[i] = (float)rot_sb((double)(i - 1) * h);
-  float* dsb;
+  // interval i: the cubic through sb((i-1)h), sb(ih), sb((i+1)h), sb((i+2)h) in f = u/h - i, as c0 + f(c1 + f(c2 + f c3))
+  std::vector<float4> sbt(ntab);
+  {
+    double tm = rot_sb(-h), t0 = rot_sb(0.0), t1 = rot_sb(h);
+    for (long long i = 0; i < ntab; ++i) {
+      const double t2 = rot_sb((double)(i + 2) * h);
+      sbt[i] = make_float4((float)t0, (float)(-tm / 3.0 - t0 / 2.0 + t1 - t2 / 6.0), (float)(tm / 2.0 - t0 + t1 / 2.0),
+                           (float)(-tm / 6.0 + t0 / 2.0 - t1 / 2.0 + t2 / 6.0));
+      tm = t0; t0 = t1; t1 = t2;
+    }
+  }
+  float4* dsb;
   rc = upload_owned(c, &dsb, sbt.data(), sbt.size()); if (rc) return rc;
   T.sbtab = dsb; T.ntab = (int)ntab; T.sb_h = h;
   T.sb_scale = 2.0 * 3.14159265358979323846 / ((double)N1 * dv1) / h;
@@ -405,7 +414,7 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     size_t win = 0;
     const char* wenv = getenv("PAYNE_ROT_WINDOW");            // "0": keep the table in L1/L2 only
     if (ok0 && occ0 >= 1 && !(wenv && wenv[0] == '0')) {
-      for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)10240, (size_t)9216, (size_t)8448, (size_t)8192, (size_t)6144,
+      for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)11008, (size_t)10880, (size_t)10752, (size_t)10496, (size_t)10240, (size_t)9216, (size_t)8448, (size_t)8192, (size_t)6144,
                           (size_t)4096, (size_t)2048}) {
         int o = 0;
         if (probe(c->tail_smem + cand, &o) && o == occ0) { win = cand; break; }
@@ -721,11 +730,11 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         if (rc) return rc;
         int cdepth = 0;
         const long long l0 = cc->launches;
-        rc = run_mlp(cc, cc->enc, th, ld, nb, cc->flux, cc->ldf, false, &cdepth, st);
+        rc = run_mlp(cc, cc->enc, th, ld, nb, cc->flux, cc->ldf, true, &cdepth, st);
         if (rc) return rc;
         if (!is_depth) return fail(PAYNE_E_UNSUPPORTED, "continuum multiply expects line-depth rows");
         ContParams C = c->contp;
-        C.cont = cc->flux; C.ldc = cc->ldf; C.flux = c->flux; C.ldf = c->ldf; C.B = nb;
+        C.cont = cc->flux; C.cont_is_depth = cdepth; C.ldc = cc->ldf; C.flux = c->flux; C.ldf = c->ldf; C.B = nb;
         if (payne::launch_continuum(std::min(nb, 8 * c->sm_count), st, C)) return fail(PAYNE_E_CUDA, "continuum launch");
         c->launches += cc->launches - l0 + 1;
       }
@@ -990,7 +999,7 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "max_batch") return c->slab;
   if (k == "sm_count") return c->sm_count;
   if (k == "tail_grid") return c->tail_grid;
-  if (k == "gauss_stencil") return c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
+  if (k == "gauss_stencil") return PAYNE_WITH_STENCIL && c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
   if (k == "rot_window_floats") return c->fast.win_floats;
   if (k == "precision") return c->lay.precision;
   if (k == "continuum") return c->cont != nullptr;

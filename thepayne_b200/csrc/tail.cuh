@@ -40,7 +40,7 @@ struct TailParams {
   const int2* back1;      // [n]   {k, bits(t)}: f_i = g[k] + t (g[k+1]-g[k])
   double sb_scale;        // 2 pi / (N1 dv1 h): table coordinate of bin k is |vsini| k sb_scale
   double sb_h;            // table spacing in u
-  const float* sbtab;     // sb(u) at u = (i-1) h, i in [0, ntab+3)
+  const float4* sbtab;    // [ntab] cubic through sb((i-1)h) .. sb((i+2)h) as Horner coefficients in f = u/h - i
   int ntab;
   // twiddles exp(-2 pi i e / Ntw), e < Ntw/2
   const float2* tw;
@@ -121,9 +121,16 @@ __device__ __forceinline__ int locate(const double* __restrict__ w, double D, do
   return j;
 }
 
-// Rotational transfer function sb(u) (smoothing.py:612-619) from a 4-point Lagrange table.
-struct RotH {
-  const float* __restrict__ tab;
+// Rotational transfer function sb(u) (smoothing.py:612-619): 4-point Lagrange interpolation of a table with
+// spacing h, stored per interval as the monomial coefficients of that cubic (one 16-byte load and three
+// FMAs per value instead of four loads and the weight polynomials).
+// WINDOW 0: global table only; 1: every interval the point can touch sits in the shared-memory copy `win`;
+// 2: the first nwin intervals do, the rest come from the global table.
+template <int WINDOW>
+struct RotHT {
+  const float4* __restrict__ tab;   // global table
+  const float4* win;                // copy of its first nwin intervals in shared memory
+  int nwin;
   double scale;     // table coordinate per bin
   double h;
   float invM;
@@ -131,15 +138,13 @@ struct RotH {
   __device__ __forceinline__ float operator()(int k) const {
     const double xt = scale * (double)k;
     const int i = (int)xt;
-    if (i + 2 >= ntab) return direct(xt * h) * invM;
+    if (WINDOW != 1 && i >= ntab) return direct(xt * h) * invM;
     const float f = (float)(xt - (double)i);
-    const float* t = tab + i;  // t[0] = sb((i-1) h)
-    const float fm1 = f - 1.f, fm2 = f - 2.f, fp1 = f + 1.f;
-    const float wm = -f * fm1 * fm2 * (1.f / 6.f);
-    const float w0 = fp1 * fm1 * fm2 * 0.5f;
-    const float w1 = -fp1 * f * fm2 * 0.5f;
-    const float w2 = fp1 * f * fm1 * (1.f / 6.f);
-    return (wm * t[0] + w0 * t[1] + w1 * t[2] + w2 * t[3]) * invM;   // global table or its shared-memory slice
+    float4 c;
+    if (WINDOW == 1) c = win[i];
+    else if (WINDOW == 2) c = i < nwin ? win[i] : __ldg(tab + i);
+    else c = __ldg(tab + i);
+    return fmaf(f, fmaf(f, fmaf(f, c.w, c.z), c.y), c.x) * invM;
   }
   static __device__ __noinline__ float direct(double u) {  // beyond the table: fp64 closed form
     if (u == 0.0) return 1.f;
@@ -148,6 +153,7 @@ struct RotH {
     return (float)(j1(u) / u - 3.0 * c / (2.0 * u * u) + 3.0 * s / (2.0 * u * u * u));
   }
 };
+using RotH = RotHT<0>;
 
 // Gaussian taper exp(-2 pi^2 sigma^2 ss^2) (smoothing.py:598-600), ss = k / (N dv).
 struct GaussH {

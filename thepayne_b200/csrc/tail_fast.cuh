@@ -22,6 +22,12 @@
 #ifndef PAYNE_TAIL_MINB
 #define PAYNE_TAIL_MINB 3
 #endif
+// The real-space stencil for the Gaussian stage (tail_stencil.cuh) is compiled in only on request
+// (-DPAYNE_WITH_STENCIL=1): measured on B200 it is no faster than the FFT convolution at C2's kernel widths,
+// and its 1.7 KB of static shared memory come out of the rotation-table window of every point.
+#ifndef PAYNE_WITH_STENCIL
+#define PAYNE_WITH_STENCIL 0
+#endif
 
 namespace payne {
 
@@ -36,7 +42,7 @@ struct FastGrid {
   const double* obs_q;                // [n_obs] (ln lambda_j - ln w_0) / dlnw
   const double* obs_otm1;             // [n_obs] (flux - 1)/eflux : r = depth/eflux - otm1
   void* points;                       // [slab] FastPoint, written by tail_setup_kernel
-  int win_floats;                     // shared-memory window for the rotation-kernel table (floats)
+  int win_floats;                     // shared-memory window for the rotation-kernel table (floats; 4 per table interval)
   float* scratch;                     // [grid, N1/2] second half of split transforms (N1 = 65536)
   TwConst twc;
 };
@@ -250,7 +256,9 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   float* zf = reinterpret_cast<float*>(smem_raw);
   __shared__ FastPoint SP;
   __shared__ double red[kNT / 32];
+#if PAYNE_WITH_STENCIL
   __shared__ StencilShared SS;
+#endif
   PointSetup& S = SP.S;
   FastSetup& FS = SP.FS;
   const int tid = threadIdx.x;
@@ -285,18 +293,20 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       // the table entries this point can touch: [0, vsini_scale * N1/2 + 3]; staged in shared
       // memory when they fit (the barrier after the regrid below publishes them)
       const double xt_max = S.vsini_scale * (double)(N1 >> 1);
-      const bool in_win = xt_max + 5.0 <= (double)min(F.win_floats, P.ntab + 3);
-      if (in_win) {
-        const int nwin = (int)xt_max + 5;
-        for (int i = tid; i < nwin; i += kNT) win[i] = __ldg(P.sbtab + i);
-      }
-      RotH H{in_win ? win : P.sbtab, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
+      // (a point whose range is longer keeps its first win_floats/4 intervals there and reads the rest
+      // from the global table)
+      float4* win4 = reinterpret_cast<float4*>(win);
+      const int nwin = (int)fmin(fmin(xt_max + 2.0, (double)(F.win_floats >> 2)), (double)P.ntab);
+      for (int i = tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);
+      // (one filter instantiation with a per-lookup choice: a second, window-only copy of the filter stage
+      // measured 1.7 % slower -- code size and register allocation at the 80-register cap)
+      const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
       // pixels stage 2 will read: its mask [i0, i1] (one more on each side keeps the edge patch exact)
       const int blo = S.use_inst ? max(S.i0 - 1, 0) : 0, bhi = S.use_inst ? min(S.i1 + 1, n - 1) : n - 1;
       if constexpr (!kSplit) {
         // regrid fused into the first FFT pass (measured against the separate regrid: tail -5 %)
         if (!(P.debug_skip & 1))
-          ct_convolve_regrid<LOG2N1 - 1>(z, tw, F.twc, H, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native);
+          ct_convolve_regrid<LOG2N1 - 1>(z, tw, F.twc, H, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native, S.clean != 0);
         if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1, blo, bhi);
       } else {
         stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
@@ -315,10 +325,13 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       GaussH H{S.taper_a, 2.0f / (float)N2};
       bool split2 = false;
       if constexpr (kSplit) split2 = (log2N2 == LOG2N1);
+#if PAYNE_WITH_STENCIL
       if (!kSplit && FS.st_R > 0) {
         // compact Gaussian: circular real-space stencil instead of the second transform pair
         acc = stage2_stencil(P, F, S, FS, zf, win, SS, row, tid, p);
-      } else if (split2) {
+      } else
+#endif
+      if (split2) {
         if constexpr (kSplit) {
           stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
           __syncthreads();
@@ -338,10 +351,10 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
           fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
         } else if (!(P.debug_skip & 2)) {
           if (log2N2 == LA)
-            ct_convolve_regrid<LA - 1>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den, FS.s_invden, F.c_native);
+            ct_convolve_regrid<LA - 1>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den, FS.s_invden, F.c_native, S.clean != 0);
           else
             ct_convolve_regrid<(LA >= 10 ? LA - 2 : 8)>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den,
-                                                         FS.s_invden, F.c_native);
+                                                         FS.s_invden, F.c_native, S.clean != 0);
         }
         if (!(P.debug_skip & 16)) acc = final_pass(P, F, S, FS, zs, tid, p, N2);
       }
@@ -406,7 +419,7 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
     // must fit the shared-memory transform buffer (no split transforms) and fill whole chunks
     const double spx = sqrt(S.sig_px2);
     const int R = (int)ceil(kStSigmas * spx);
-    if (P.gauss_stencil && !P.rows_may_nan && spx >= kStMinSigmaPx && R <= kStMaxR && S.log2N2 >= 11 && S.log2N2 <= 15 &&
+    if (PAYNE_WITH_STENCIL && P.gauss_stencil && !P.rows_may_nan && spx >= kStMinSigmaPx && R <= kStMaxR && S.log2N2 >= 11 && S.log2N2 <= 15 &&
         F.win_floats >= kStSideFloats) {
       const int E = (R + 2) / 2;                       // offsets 2e-1, 2e, 2e+1 must cover [-R, R]
       FS.st_R = R;
