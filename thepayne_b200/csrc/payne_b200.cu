@@ -232,6 +232,10 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
   T.lnw0 = std::log(w[0]);
   T.inv_dlnw = (double)(n - 1) / (std::log(w[n - 1]) - std::log(w[0]));
   T.sigma_in = kCkms / s->resolution;
+  {
+    const char* e = getenv("PAYNE_DISCARD_ROWS");            // "0": leave the consumed rows to L2's write-back
+    T.discard_rows = !(e && e[0] == '0');
+  }
   T.inst_scale = kFwhmFit;
   {
     // Opt-in ("1"): measured on B200 at C2 (sigma 3.8-5.6 px, 49-71 taps) the stencil's inner loop alone
@@ -1039,6 +1043,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)
   if (k == "gauss_stencil") { c->tail.gauss_stencil = value != 0; return PAYNE_OK; }
+  if (k == "discard_rows") { c->tail.discard_rows = value != 0; return PAYNE_OK; }
   if (k == "rows_may_nan") { c->tail.rows_may_nan = value != 0; return PAYNE_OK; }
   if (k == "inst_r_is_sigma") { c->tail.inst_scale = value ? 1.0 : payne::kFwhmFit; return PAYNE_OK; }   // profiling aid, see tail.cuh
   return fail(PAYNE_E_INVALID, "unknown key " + k);

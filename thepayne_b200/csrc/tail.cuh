@@ -76,6 +76,7 @@ struct TailParams {
   int B;
   int gauss_stencil;        // fast tail: instrumental broadening as a real-space stencil when the kernel is compact
   double inst_scale;        // Inst_R -> sigma-resolution: 2.355 (genmod.py:83, FWHM given) or 1 (getspec callers)
+  int discard_rows;         // fast tail: drop a consumed row's lines from L2 without write-back (discard.global.L2)
   int rows_may_nan;         // rows can hold NaN although the labels are finite (continuum emulator attached)
   int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
                             // bit3 the regrid back, bit4 the final pass; results are garbage
@@ -135,11 +136,19 @@ struct RotHT {
   double h;
   float invM;
   int ntab;
+  // Table position of bin k in 24.40 fixed point (k < 2^15, scale < 2^8): one wide integer multiply, a shift
+  // and an int->float conversion instead of four double-precision conversions per value; the position is
+  // good to 2^-28 of a table interval.
+  unsigned long long s40;
+  __device__ static unsigned long long fix40(double scale) {
+    return scale < 256.0 ? (unsigned long long)__double2ll_rn(scale * 1099511627776.0) : ~0ull;
+  }
   __device__ __forceinline__ float operator()(int k) const {
-    const double xt = scale * (double)k;
-    const int i = (int)xt;
-    if (WINDOW != 1 && i >= ntab) return direct(xt * h) * invM;
-    const float f = (float)(xt - (double)i);
+    if (s40 == ~0ull) return direct(scale * (double)k * h) * invM;     // absurdly broad kernel: closed form
+    const unsigned long long pos = (unsigned long long)(unsigned)k * s40;
+    const int i = (int)(pos >> 40);
+    if (WINDOW != 1 && i >= ntab) return direct(scale * (double)k * h) * invM;
+    const float f = (float)(unsigned)(pos >> 8) * 2.3283064365386963e-10f;   // low 32 of the 40 fraction bits
     float4 c;
     if (WINDOW == 1) c = win[i];
     else if (WINDOW == 2) c = i < nwin ? win[i] : __ldg(tab + i);

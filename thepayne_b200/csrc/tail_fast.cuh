@@ -162,21 +162,35 @@ __device__ __forceinline__ void stage_regrid(const PointSetup& S, const float* r
 template <class ZV>
 __device__ __forceinline__ void regrid_back(float* row, const ZV& zv, const FastGrid& F, int tid, int n, int N1,
                                             int ilo, int ihi) {
-  const long long v0 = (long long)(ilo + tid) * F.b_num;
+  // interior pixels [1, n-2] only: no edge tests and no clamp of k + 1 in the loop (pixel n-1 is the only one
+  // that sits on the last grid point); the two end pixels are the patch of predictspec.py:240-241
+  const int lo = max(ilo, 1), hi = min(ihi, n - 2);
+  const long long v0 = (long long)(lo + tid) * F.b_num;
   int k = (int)(v0 / F.b_den);
   int rem = (int)(v0 - (long long)k * F.b_den);
+  const int den = F.b_den, incj = F.b_incj, incr = F.b_incr;
+  const float invden = F.b_invden, cg = F.c_grid1;
 #pragma unroll 4
-  for (int i = ilo + tid; i <= ihi; i += kNT) {
-    const float dl = (float)rem * F.b_invden;
-    const float g0 = zv.ld(k), g1 = zv.ld(min(k + 1, N1 - 1));
-    const float v = fmaf(interp_w(dl, F.c_grid1), g1 - g0, g0);
-    if (i > 0 && i < n - 1) {
-      row[i] = v;
-      if (i == 1) row[0] = v;
-      if (i == n - 2) row[n - 1] = v;
-    }
-    k += F.b_incj; rem += F.b_incr;
-    if (rem >= F.b_den) { rem -= F.b_den; ++k; }
+  for (int i = lo + tid; i <= hi; i += kNT) {
+    const float dl = (float)rem * invden;
+    const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
+    row[i] = fmaf(interp_w(dl, cg), g1 - g0, g0);
+    k += incj; rem += incr;
+    if (rem >= den) { rem -= den; ++k; }
+  }
+  if (tid == 0 && ilo == 0) {
+    const long long v1 = F.b_num;                         // pixel 1
+    const int k1 = (int)(v1 / den);
+    const float d1 = (float)(int)(v1 - (long long)k1 * den) * invden;
+    const float a = zv.ld(k1), b = zv.ld(k1 + 1);
+    row[0] = fmaf(interp_w(d1, cg), b - a, a);
+  }
+  if (tid == 32 && ihi == n - 1) {
+    const long long v1 = (long long)(n - 2) * F.b_num;    // pixel n-2
+    const int k1 = (int)(v1 / den);
+    const float d1 = (float)(int)(v1 - (long long)k1 * den) * invden;
+    const float a = zv.ld(k1), b = zv.ld(k1 + 1);
+    row[n - 1] = fmaf(interp_w(d1, cg), b - a, a);
   }
 }
 
@@ -246,6 +260,16 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
 #include "tail_stencil.cuh"
 namespace payne {
 
+// Drop the L2 lines lying wholly inside row[0, n) without write-back.  Not inlined on purpose: the tail kernel
+// sits at its 80-register cap, and these few instructions inlined at the end of the point loop changed the
+// allocation of the whole kernel (+1.5 % time).
+static __device__ __noinline__ void discard_lines(const float* row, int n, int tid) {
+  const unsigned long long a0 = (unsigned long long)row, a1 = a0 + 4ull * (unsigned long long)n;
+  const unsigned long long last = a1 & ~127ull;
+  for (unsigned long long a = ((a0 + 127ull) & ~127ull) + 128ull * (unsigned)tid; a < last; a += 128ull * kNT)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a));
+}
+
 // LOG2N1 <= 15: the whole transform sits in shared memory (3 CTAs/SM up to 2^14).
 // LOG2N1 == 16: split transform, half in shared memory (128 KB), half in the scratch line.
 template <int LOG2N1>
@@ -300,7 +324,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       for (int i = tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);
       // (one filter instantiation with a per-lookup choice: a second, window-only copy of the filter stage
       // measured 1.7 % slower -- code size and register allocation at the 80-register cap)
-      const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab};
+      const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab, RotHT<2>::fix40(S.vsini_scale)};
       // pixels stage 2 will read: its mask [i0, i1] (one more on each side keeps the edge patch exact)
       const int blo = S.use_inst ? max(S.i0 - 1, 0) : 0, bhi = S.use_inst ? min(S.i1 + 1, n - 1) : n - 1;
       if constexpr (!kSplit) {
@@ -391,6 +415,12 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       if (P.chi2_sed) c2 += P.chi2_sed[p];
       P.lnl[p] = -0.5 * c2;
     }
+    // The row is scratch and fully consumed: L2 is told to drop its lines instead of writing them back
+    // (discard.global.L2).  Without this every row crosses HBM three times (the emulator's write is evicted --
+    // the slab is larger than L2 --, the tail reads it, and the in-place rewrite after the rotation stage is
+    // evicted again): measured DRAM traffic of the tail 456 MB = 2.0x the algorithmic bytes, 254 MB = 1.09x
+    // with the discard, for +1.4 % of kernel time.  Only lines that lie wholly inside this row are dropped.
+    if (P.discard_rows) discard_lines(row, P.n, tid);
     __syncthreads();
   }
 }

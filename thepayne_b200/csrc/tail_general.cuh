@@ -62,7 +62,7 @@ tail_general_kernel(const __grid_constant__ TailParams P, const __grid_constant_
         zf[zidx(k)] = a + t * (b - a);
       }
       __syncthreads();
-      RotH H{P.sbtab, nullptr, 0, S.vsini_scale, P.sb_h, 1.0f / (float)(1 << log2M), P.ntab};
+      RotH H{P.sbtab, nullptr, 0, S.vsini_scale, P.sb_h, 1.0f / (float)(1 << log2M), P.ntab, RotH::fix40(S.vsini_scale)};
       convolve_any<LOG2N1>(z, P.log2N1, tw, TC, H, tid);
       // back onto the emulator grid + the edge patch of predictspec.py:240-241
       const int n = P.n;

@@ -123,7 +123,7 @@ tail_lsf_kernel(const __grid_constant__ TailParams P, const __grid_constant__ Ls
         zf[zidx(k)] = a + t * (b - a);
       }
       __syncthreads();
-      RotH H{P.sbtab, nullptr, 0, S.vsini_scale, P.sb_h, 1.0f / (float)(1 << log2M), P.ntab};
+      RotH H{P.sbtab, nullptr, 0, S.vsini_scale, P.sb_h, 1.0f / (float)(1 << log2M), P.ntab, RotH::fix40(S.vsini_scale)};
       FftPlan plan; plan.make(log2M);
       fft_forward(z, log2M, plan, twr, tid, kTailThreads);
       filter_pairs(z, log2M, plan, twr, H, tid, kTailThreads);
