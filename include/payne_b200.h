@@ -88,8 +88,9 @@ enum {
  *             trainspec_multi.py:29-52); W[0] = [n_groups,H1,D_in], W[1], W[2] = [n_groups,H1,H1], W[3] =
  *             [D_out,H1] (the chunks' output layers one after another), biases alike; H2 = H3 = H1;
  *             encode_offset 0 (trainspec_multi.py:56-67).
- * The leaky-ReLU stacks run on the CUDA-core fp32 kernels whatever PayneLayout.precision says
- * (the tensor-core operand slicing needs activations in [0,1)). */
+ * The leaky-ReLU stacks keep their (narrow) hidden layers on the CUDA-core fp32 kernels; in PARITY mode their wide
+ * output layer -- nearly all of their flops -- runs on the tensor cores with row-scaled operand slices (activations
+ * divided by the power of two above the row maximum; contraction width <= 512), SIMT_FP32 keeps everything on CUDA cores. */
 enum { PAYNE_ACT_SIGMOID = 0, PAYNE_ACT_LEAKY_RELU = 1 };
 typedef struct {
   int32_t D_in, H1, H2, H3, D_out;
@@ -180,7 +181,8 @@ int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, 
                    void* stream);
 
 /* Introspection for benches/tests: key is one of "n_ann","n_obs","nfft1","launches",
- * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","continuum","lsf","status"
+ * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","continuum","lsf","legacy_tc"
+ * (a leaky-ReLU stack whose output layer runs on the tensor cores),"status"
  * (bit0: a point needed a larger transform than the shared-memory carve-out). Returns the value or -1. */
 int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
 /* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points), "timing" (0/1,

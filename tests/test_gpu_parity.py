@@ -351,3 +351,28 @@ def test_gauss_stencil_agrees_with_fft_stage():
         np.testing.assert_array_equal(np.nan_to_num(la, nan=7.0), np.nan_to_num(la2, nan=7.0))
         assert eng.query('status') == 0
         eng.close()
+
+
+@pytest.mark.parametrize('name', ['mini_smlp', 'mini_yst'])
+def test_legacy_output_layer_on_tensor_cores(name):
+    """SMLP / YST1 in parity mode: hidden layers on CUDA cores, the wide output layer as a row-scaled
+    exact-accumulation GEMM on the tensor cores (mlp_tc.cuh x3_split_rows_kernel).  Same spectra as the all-CUDA-core
+    mode to fp32 round-off, and the emulator alone against the oracle's own evaluation of the net."""
+    cfg, g = load_case(name)
+    th = torch.from_numpy(np.ascontiguousarray(np.vstack([g['theta'], cfg.draw(40, seed=2)]))).cuda()
+    out = {}
+    for prec in ('parity', 'simt'):
+        eng = _engine(cfg, prec)
+        assert eng.query('legacy_tc') == (1 if prec == 'parity' else 0)
+        f, _, l = eng.model_batch(th)
+        y = eng.ann_eval(th[:, :cfg.spec.D_in].contiguous())
+        out[prec] = (f.cpu().numpy(), l.cpu().numpy(), y.cpu().numpy())
+        assert eng.query('status') == 0
+        eng.close()
+    fa, la, ya = out['parity']
+    fb, lb, yb = out['simt']
+    assert np.array_equal(np.isnan(fa), np.isnan(fb))
+    fin = np.isfinite(fb)
+    assert np.max(np.abs(fa[fin] - fb[fin]) / np.abs(fb[fin])) <= 2.5e-7
+    yo = O.make_net(cfg.spec)(th[:, :cfg.spec.D_in].cpu().numpy())
+    assert np.max(np.abs(ya - yo) / np.abs(yo)) <= 5e-7 and np.max(np.abs(yb - yo) / np.abs(yo)) <= 1e-6

@@ -35,6 +35,12 @@ int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out
                          prec, sm_count, st, launches, out_rows);
 }
 
+int tc_run_scaled_layer_x(const TcWeights& w, const float* bias, const float* h, long long ldh, TcActs* acts,
+                          float* rscale, int nb, float* out, long long ldo, float bias_shift, int sm_count,
+                          cudaStream_t st, long long* launches) {
+  return tc_run_scaled_layer(w, bias, h, ldh, acts, rscale, nb, out, ldo, bias_shift, sm_count, st, launches);
+}
+
 int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& a, const TcWeights& w,
                    const float* db, float* dC, int sm_count) {
   const unsigned blocks = (unsigned)(((long long)M * K + 255) / 256);

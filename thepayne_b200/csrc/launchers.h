@@ -26,6 +26,10 @@ int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out
                       TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out, long long ldo,
                       float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
                       long long out_rows);
+// output layer of a leaky-ReLU stack from fp32 activations of any sign / magnitude (row-scaled slices)
+int tc_run_scaled_layer_x(const TcWeights& w, const float* bias, const float* h, long long ldh, TcActs* acts,
+                          float* rscale, int nb, float* out, long long ldo, float bias_shift, int sm_count,
+                          cudaStream_t st, long long* launches);
 // unit-test GEMM: slices dA [M, K] into the operand planes of `a`, then C = A . W^T + bias
 int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& a, const TcWeights& w,
                    const float* dbias, float* dC, int sm_count);

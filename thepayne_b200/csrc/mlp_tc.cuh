@@ -257,7 +257,7 @@ constexpr int kRowBytes = 128;   // one swizzle row: 32 tf32 or 64 bf16 along K
 template <bool X3>
 __device__ __forceinline__ void epi_store_block(const CUtensorMap* cmap, float* stage, const float* sb,
                                                 const float* ss, const uint32_t (&v)[32], const uint32_t (&c)[32],
-                                                int colbase, int gcol0, int grow0, int lane) {
+                                                int colbase, int gcol0, int grow0, int lane, float rs = 1.f) {
   if (lane == 0) ptx::tma_store_wait_read();      // the previous store has finished reading the block
   __syncwarp();
   float4* st4 = reinterpret_cast<float4*>(stage) + lane * 8;
@@ -268,10 +268,11 @@ __device__ __forceinline__ void epi_store_block(const CUtensorMap* cmap, float* 
     const float4 bb = b4[k], sc = s4[k];
     float4 o;
     if (X3) {
-      o.x = fmaf(__uint_as_float(v[4 * k + 0]) + __uint_as_float(c[4 * k + 0]), sc.x, bb.x);
-      o.y = fmaf(__uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1]), sc.y, bb.y);
-      o.z = fmaf(__uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]), sc.z, bb.z);
-      o.w = fmaf(__uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]), sc.w, bb.w);
+      // rs and sc are powers of two: the products below are exact, the FMA rounds once
+      o.x = fmaf((__uint_as_float(v[4 * k + 0]) + __uint_as_float(c[4 * k + 0])) * rs, sc.x, bb.x);
+      o.y = fmaf((__uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1])) * rs, sc.y, bb.y);
+      o.z = fmaf((__uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2])) * rs, sc.z, bb.z);
+      o.w = fmaf((__uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3])) * rs, sc.w, bb.w);
     } else {
       o.x = __uint_as_float(v[4 * k + 0]) + bb.x; o.y = __uint_as_float(v[4 * k + 1]) + bb.y;
       o.z = __uint_as_float(v[4 * k + 2]) + bb.z; o.w = __uint_as_float(v[4 * k + 3]) + bb.w;
@@ -336,6 +337,8 @@ struct TcCfg {
 struct TcGemmArgs {
   const float* bias;
   const float* wscale;  // X3: per output column power-of-two scale
+  const float* rscale;  // EPI 0, X3: per output ROW power-of-two scale of the A operand (null = 1): rows whose
+                        // activations are not confined to [0,1) are sliced as h / rscale (x3_split_rows_kernel)
   void* out0;           // EPI 0: fp32 C ; EPI 1: plane 0 of the next layer's operand
   void* out1;
   void* out2;
@@ -512,6 +515,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
       const int row_base = m0 + q * 32;
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols);
       if constexpr (EPI == 0) {
+        const float rs = (MODE == kModeX3 && G.rscale && row_base + lane < G.M) ? __ldg(G.rscale + row_base + lane) : 1.f;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           const int col0 = n0 + ch * 32;
@@ -520,7 +524,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
           ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
           if constexpr (MODE == kModeX3) ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
           ptx::tmem_ld_wait();
-          epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, gcol + col0, row_base, lane);
+          epi_store_block<MODE == kModeX3>(&T.c, pt, sbias, sscale, v, c, ch * 32, gcol + col0, row_base, lane, rs);
         }
       } else if constexpr (kRegEpi) {
         // Hidden layer: thread = row.  Its 32 accumulator columns never leave registers:
@@ -830,6 +834,40 @@ static __global__ void x3_split_kernel(const float* __restrict__ src, long long 
   p1[r * ldd + c] = a; p2[r * ldd + c] = b; p3[r * ldd + c] = d;
 }
 
+// Rows that are not confined to [0,1) (leaky-ReLU activations): one warp per row finds s = the power of two >= max|h|
+// of the row, writes it to rscale and slices h / s (|h / s| <= 1, signed slices: the magic-number rounding of
+// x3_split_act is sign-agnostic and bf16 holds the integers up to 256 exactly).  The leading product sum stays exact
+// for K <= 512 (|p1 q1| <= 1, grid 2^-15).  Precision is 2^-24 of the ROW maximum rather than of each element, which
+// for a dot product is what an fp32 GEMM's own rounding amounts to.
+static __global__ void __launch_bounds__(256)
+x3_split_rows_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ p1,
+                     __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, long long ldd,
+                     float* __restrict__ rscale, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (r >= rows) return;
+  const float* h = src + (long long)r * lds;
+  float mx = 0.f;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, fabsf(h[c]));      // fmaxf drops NaN: those rows come out NaN anyway
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s = 1.f;
+  if (mx > 0.f && mx < 3.0e38f) {
+    int e;
+    const float m = frexpf(mx, &e);                  // mx = m 2^e, 0.5 <= m < 1
+    s = ldexpf(1.f, (m == 0.5f) ? e - 1 : e);        // smallest power of two >= mx
+  }
+  if (lane == 0) rscale[r] = s;
+  const float inv = 1.f / s;                          // exact
+  for (int c = lane; c < cols; c += 32) {
+    __nv_bfloat16 a, b, d;
+    x3_split_act(h[c] * inv, a, b, d);
+    const long long o = (long long)r * ldd + c;
+    p1[o] = a; p2[o] = b; p3[o] = d;
+  }
+}
+
 // Label encode + first layer + fixed-point slicing in one pass (parity mode): one warp per point.
 // Lane i < D_in encodes label i once (fp64, NNmodels.py:164-168) and the warp shares the result;
 // each lane then forms outputs h = lane, lane + 32, ... with the same fmaf order as
@@ -1021,7 +1059,7 @@ template <int BN, int MODE, int EPI, int MC>
 inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                           void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
                           TcMapCache* cache = nullptr, long long map_rows = 0, const TcGroups* grp = nullptr,
-                          int out_cols = 0) {
+                          int out_cols = 0, const float* rscale = nullptr) {
   using Cfg = TcCfg<BN, MODE>;
   static_assert(Cfg::kStages >= 2, "ring too shallow");
   constexpr int kVariant = BN * 1000 + MODE * 100 + EPI * 10 + MC;
@@ -1059,7 +1097,7 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
                              Cfg::kSmem) != cudaSuccess) return PAYNE_E_CUDA;
     if (dev < 64) attr_set |= 1ull << dev;
   }
-  TcGemmArgs G{bias, W.scale, out0, out1, out2, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
+  TcGemmArgs G{bias, W.scale, rscale, out0, out1, out2, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
   if (grouped) {
     G.N = grp->n; G.groups = grp->groups; G.n_last = grp->n_last; G.a_grows = grp->a_grows; G.b_grows = grp->n;
     G.out_gstride = grp->out_gstride;
@@ -1118,7 +1156,7 @@ inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float
       return PAYNE_E_CUDA;
     if (dev < 64) attr_set |= 1ull << dev;
   }
-  TcGemmArgs G{bias, W.scale, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
+  TcGemmArgs G{bias, W.scale, nullptr, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
   const int pair_tiles = ((M + 255) / 256) * ((W.N + BN - 1) / BN);
   const int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
   cudaLaunchConfig_t cfg{};
@@ -1135,7 +1173,10 @@ template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                      void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
                      TcMapCache* cache = nullptr, long long map_rows = 0, const TcGroups* grp = nullptr,
-                     int out_cols = 0) {
+                     int out_cols = 0, const float* rscale = nullptr) {
+  if (rscale)      // scaled rows (leaky-ReLU nets): the plain single-CTA kernel
+    return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
+                                            map_rows, grp, out_cols, rscale);
   if (grp && grp->groups > 1)
     return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
                                             map_rows, grp, out_cols);
@@ -1248,6 +1289,22 @@ inline int tc_run_multinet(const TcWeights* tcw, float* const* bias, int H, int 
     default:
       return PAYNE_E_UNSUPPORTED;
   }
+}
+
+// Output layer of a leaky-ReLU stack (SMLP / YST1) on the tensor cores: fp32 activations h [nb, K] (any sign and
+// magnitude) -> row-scaled slices -> out = h . W^T + bias (+ bias_shift), exact-accumulation split.
+inline int tc_run_scaled_layer(const TcWeights& w, const float* bias, const float* h, long long ldh, TcActs* acts,
+                               float* rscale, int nb, float* out, long long ldo, float bias_shift, int sm_count,
+                               cudaStream_t st, long long* launches) {
+  if (!w.xplane[0] || w.K > kX3MaxK) return PAYNE_E_UNSUPPORTED;
+  x3_split_rows_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(h, ldh, (__nv_bfloat16*)acts->plane[0],
+                                                                 (__nv_bfloat16*)acts->plane[1],
+                                                                 (__nv_bfloat16*)acts->plane[2], acts->ld, rscale, nb, w.K);
+  ++*launches;
+  const int rc = tc_launch<PAYNE_LIN6_BN, kModeX3, 0>(*acts, w.K, w, bias, out, nullptr, nullptr, ldo, bias_shift, nb, sm_count,
+                                                      st, nullptr, 0, nullptr, 0, rscale);
+  ++*launches;
+  return rc;
 }
 
 // lin2..lin6 from the fp32 output of lin1 (h1, pitch = dims_out[0]).  bias_shift is added to the

@@ -118,7 +118,9 @@ struct PayneCtx {
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;   // used by the *_host entry
   int n_layers = 6;
-  bool legacy = false;             // leaky-ReLU stack (SMLP / YST1): CUDA-core fp32 layers only
+  bool legacy = false;             // leaky-ReLU stack (SMLP / YST1): hidden layers on the CUDA-core fp32 kernels
+  bool legacy_tc = false;          // ... and the wide output layer on the tensor cores (row-scaled slices, parity mode)
+  float* rscale = nullptr;         // [slab] per-row scale of that layer's operand (workspace)
   // multi-chunk emulator (trainspec_multi.py:29-52): n_groups sigmoid nets of 4 layers, `chunk` pixels each
   bool multinet = false;
   int n_groups = 1, chunk = 0;
@@ -531,6 +533,12 @@ int build_spec(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs, bool emu
     if (rc) return fail(rc, "tc_prepare_weights failed");
     return PAYNE_OK;
   }
+  // leaky-ReLU stacks: the output layer (nearly all of their flops) takes row-scaled slices, K <= 512
+  if (c->legacy && din[nl - 1] <= payne::kX3MaxK && din[nl - 1] >= 8) {
+    rc = payne::tc_prepare_weights_x(&c->tcw[nl - 1], s->W[nl - 1], dout[nl - 1], din[nl - 1], &c->owned);
+    if (rc) return fail(rc, "tc_prepare_weights failed");
+    c->legacy_tc = true;
+  }
   // tensor-core operand copies of the weights (sigmoid LinNet only)
   for (int k = 1; k < 6 && !c->legacy; ++k) {
     rc = payne::tc_prepare_weights_x(&c->tcw[k], s->W[k], dout[k], din[k], &c->owned);
@@ -578,8 +586,8 @@ int ensure_workspace(PayneCtx* c, long long B) {
   const long long need = std::min(B, c->slab);
   if (need <= c->slab_alloc) return PAYNE_OK;
   auto drop = [&](void* p) { if (p) cudaFree(p); };
-  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
-  c->fast.points = nullptr;
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points); drop(c->rscale);
+  c->fast.points = nullptr; c->rscale = nullptr;
   payne::tc_free_acts_x(&c->actA); payne::tc_free_acts_x(&c->actB);
   c->flux = c->hA = c->hB = nullptr; c->chi2_sed = nullptr; c->slab_alloc = 0;
   const long long rows = (need + 127) / 128 * 128;
@@ -591,6 +599,7 @@ int ensure_workspace(PayneCtx* c, long long B) {
     CU_TRY(cudaMemset(c->flux, 0, (size_t)rows * c->ldf * sizeof(float)));   // the row padding stays zero
     CU_TRY(cudaMalloc((void**)&c->hA, (size_t)arows * hmax * sizeof(float)));
     CU_TRY(cudaMalloc((void**)&c->hB, (size_t)arows * hmax * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&c->rscale, (size_t)rows * sizeof(float)));
     CU_TRY(cudaMalloc(&c->fast.points, (size_t)rows * sizeof(payne::FastPoint)));
     CU_TRY(cudaMemset(c->fast.points, 0, (size_t)rows * sizeof(payne::FastPoint)));   // struct padding is copied too
     int rc = payne::tc_alloc_acts_x(&c->actA, arows, hmax); if (rc) return fail(rc, "tc_alloc_acts");
@@ -670,6 +679,13 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
         else
           sgemm_bias_act_kernel<kActSigmoid><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], nxt, N, nb, N, K, 0.f);
         std::swap(cur, nxt);
+      } else if (c->legacy && c->legacy_tc && prec == PAYNE_PREC_PARITY && (ldo & 3) == 0 && ((uintptr_t)out & 15) == 0) {
+        // the wide output layer on the tensor cores: row-scaled exact-accumulation split (mlp_tc.cuh)
+        int rc = tc_run_scaled_layer_x(c->tcw[k], c->b[k], cur, K, &c->actA, c->rscale, nb, out, ldo,
+                                       want_depth ? -1.f : 0.f, c->sm_count, st, &c->launches);
+        if (rc) return fail(rc, "tensor-core output layer failed");
+        *is_depth = want_depth ? 1 : 0;
+        c->launches--;                       // counted below
       } else {
         sgemm_bias_act_kernel<kActNone><<<grid, 256, 0, st>>>(cur, K, c->W[k], c->b[k], out, ldo, nb, N, K,
                                                               want_depth ? -1.f : 0.f);
@@ -828,7 +844,7 @@ void payne_ctx_destroy(PayneCtx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->owned) cudaFree(p);
   auto drop = [&](void* p) { if (p) cudaFree(p); };
-  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points);
+  drop(c->flux); drop(c->hA); drop(c->hB); drop(c->chi2_sed); drop(c->fast.points); drop(c->rscale);
   c->fast.points = nullptr; drop(c->status);
   payne::tc_free_acts_x(&c->actA); payne::tc_free_acts_x(&c->actB);
   drop(c->theta_stage); drop(c->lnl_stage);
@@ -1006,6 +1022,7 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "gauss_stencil") return PAYNE_WITH_STENCIL && c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
   if (k == "rot_window_floats") return c->fast.win_floats;
   if (k == "precision") return c->lay.precision;
+  if (k == "legacy_tc") return c->legacy && c->legacy_tc && c->lay.precision == PAYNE_PREC_PARITY;
   if (k == "continuum") return c->cont != nullptr;
   if (k == "lsf") return c->lsf_on;
   if (k == "status") {
