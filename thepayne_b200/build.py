@@ -23,6 +23,7 @@ UNITS = {
     'payne_b200.cu': ['mlp_simt.cuh', 'mlp_tc_types.h'] + _FAST + ['launchers.h', 'phot.cuh', 'continuum.cuh', 'tail_lsf.cuh'],
     'gemm_tu.cu': _GEMM + ['mlp_tc_types.h', 'launchers.h'],
     'tail_fast_tu.cu': _FAST + ['launchers.h'],
+    'tail_cluster_tu.cu': _FAST + ['tail_cluster.cuh', 'launchers.h'],
     'tail_general_tu.cu': _FFT + ['tail_general.cuh', 'tail_lsf.cuh', 'continuum.cuh', 'launchers.h'],
 }
 

@@ -41,6 +41,11 @@ bool probe_tail_fast(int l2, size_t smem_bytes, int* ctas_per_sm);
 int launch_tail_fast(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
 int launch_tail_setup(int nb, cudaStream_t st, const TailParams& T, const FastGrid& F);
 
+// ---- tail_cluster_tu.cu: the same tail with one transform spread over a cluster of four CTAs (tail_cluster.cuh;
+// emulator grids above 16384 pixels).  max_clusters = co-resident clusters on the device.
+bool probe_tail_cluster(int l2, size_t smem_bytes, int* ctas_per_sm, int* max_clusters);
+int launch_tail_cluster(int l2, int n_clusters, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+
 // ---- tail_general_tu.cu: any increasing grid (tail_general.cuh), LSF-vector broadening (tail_lsf.cuh)
 bool probe_tail_general(int l2, size_t smem_bytes, int* ctas_per_sm);
 int launch_tail_general(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const TwConst& tc);

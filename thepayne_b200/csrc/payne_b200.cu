@@ -148,6 +148,10 @@ struct PayneCtx {
   int grid_loguniform = 0;
   int use_fast = 0;        // analytic-regrid tail selected (log-uniform emulator grid)
   int allow_fast = 1;
+  // cluster-distributed fast tail (tail_cluster.cuh) for transforms above 16384 samples
+  int use_cluster = 0, allow_cluster = 1;
+  size_t cluster_smem = 0;
+  int cluster_win_floats = 0, cluster_n = 0, cluster_occ = 0;
   // continuum emulator (predictspec.py:96-102, 208-226): a second emulator context (weights, operand
   // planes, its own output rows) and the per-dataset tables of the multiply
   PayneCtx* cont = nullptr;
@@ -401,6 +405,9 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     rc = upload_owned(c, &dq, oq.data(), no); if (rc) return rc;
     rc = upload_owned(c, &dot, oot.data(), no); if (rc) return rc;
     F.obs_q = dq; F.obs_otm1 = dot;
+    F.obs_sorted = 1;
+    for (int j = 0; j < no; ++j)
+      if (!std::isfinite(ow[j]) || (j > 0 && ow[j] < ow[j - 1])) F.obs_sorted = 0;
     for (int set = 0; set < 2; ++set)
       for (int ip = 0; ip < 4; ++ip)
         for (int q = 0; q < 16; ++q) {
@@ -436,6 +443,32 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
       c->owned.push_back(sc);
       c->fast.scratch = sc;
     }
+    // Transforms above 16384 samples: one transform spread over a cluster of four CTAs (an eighth of the packed
+    // signal each, three CTAs per SM) instead of one CTA per SM holding all (32768) or half (65536) of it.
+    const char* cenv = getenv("PAYNE_TAIL_CLUSTER");         // "0": keep the single-CTA kernels
+    if (l2 >= 15 && !(cenv && cenv[0] == '0')) {
+      const size_t base = (size_t)N1;                         // N1/8 complex points of 8 bytes per CTA
+      int occ0 = 0, ncl0 = 0;
+      if (payne::probe_tail_cluster(l2, base, &occ0, &ncl0) && occ0 >= 1 && ncl0 >= 1) {
+        size_t win = 0;
+        const char* wenv = getenv("PAYNE_ROT_WINDOW");
+        if (!(wenv && wenv[0] == '0'))
+          for (size_t cand : {(size_t)32768, (size_t)16384, (size_t)12288, (size_t)11008, (size_t)10880, (size_t)10752, (size_t)10496,
+                              (size_t)10240, (size_t)9216, (size_t)8448, (size_t)8192, (size_t)6144, (size_t)4096, (size_t)2048}) {
+            int o = 0, ncl = 0;
+            if (payne::probe_tail_cluster(l2, base + cand, &o, &ncl) && o == occ0 && ncl == ncl0) { win = cand; break; }
+          }
+        int occ = 0, ncl = 0;
+        if (payne::probe_tail_cluster(l2, base + win, &occ, &ncl) && ncl >= 1) {
+          c->use_cluster = 1;
+          c->cluster_smem = base + win;
+          c->cluster_win_floats = (int)(win / 4);
+          c->cluster_n = ncl;
+          c->cluster_occ = occ;
+        }
+      }
+    }
+    c->fast.cluster = c->use_cluster;
   }
   if (l2 <= 15) {
     int occ = 0;
@@ -776,6 +809,11 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         TL.col[PAYNE_P_INSTR] = -1;                                   // the vector replaces Inst_R
         TL.fixed[PAYNE_P_INSTR] = std::numeric_limits<double>::quiet_NaN();
         if (payne::launch_tail_lsf(std::min(c->lsf_grid, nb), c->lsf_smem, st, TL, c->lsf)) return fail(PAYNE_E_CUDA, "tail launch");
+      } else if (fast_tail && is_depth && c->use_cluster && c->allow_cluster) {
+        payne::FastGrid FC = c->fast;
+        FC.win_floats = c->cluster_win_floats;
+        if (payne::launch_tail_cluster(T.log2N1, (int)std::min<long long>(c->cluster_n, nb), c->cluster_smem, st, T, FC))
+          return fail(PAYNE_E_CUDA, "tail launch");
       } else if (fast_tail && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
         if (payne::launch_tail_fast(T.log2N1, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
@@ -1021,6 +1059,9 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "tail_grid") return c->tail_grid;
   if (k == "gauss_stencil") return PAYNE_WITH_STENCIL && c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
   if (k == "rot_window_floats") return c->fast.win_floats;
+  if (k == "tail_cluster") return c->use_fast && c->allow_fast && c->use_cluster && c->allow_cluster;
+  if (k == "tail_clusters") return c->cluster_n;
+  if (k == "tail_cluster_ctas_per_sm") return c->cluster_occ;
   if (k == "precision") return c->lay.precision;
   if (k == "legacy_tc") return c->legacy && c->legacy_tc && c->lay.precision == PAYNE_PREC_PARITY;
   if (k == "continuum") return c->cont != nullptr;
@@ -1056,6 +1097,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   }
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
+  if (k == "tail_cluster") { c->allow_cluster = value != 0; return PAYNE_OK; }
   if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)

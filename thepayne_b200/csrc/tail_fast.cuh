@@ -44,6 +44,8 @@ struct FastGrid {
   void* points;                       // [slab] FastPoint, written by tail_setup_kernel
   int win_floats;                     // shared-memory window for the rotation-kernel table (floats; 4 per table interval)
   float* scratch;                     // [grid, N1/2] second half of split transforms (N1 = 65536)
+  int obs_sorted;                     // observed wavelengths are non-decreasing (cluster tail: pixel ranges per CTA)
+  int cluster;                        // the cluster tail (tail_cluster.cuh) is in use: tail_setup fills FastSetup::jcut
   TwConst twc;
 };
 
@@ -54,6 +56,8 @@ struct FastSetup {
   int st_e4, st_n4;                   // first coefficient step (in units of 4) and number of 4-step groups
   double st_inv2s2;                   // 1 / (2 sigma_px^2)
   double q0, scale;                   // final: p = (obs_q - q0) * scale
+  int jcut[3];                        // cluster tail: first observed pixel at or beyond sample (r+1) N2/4 (sorted pixels)
+  int pad_;
 };
 
 // Per-point setup, computed by tail_setup_kernel (one thread per point) ahead of the tail so that
@@ -456,6 +460,18 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
       FS.st_e4 = -((E + 3) / 4);
       FS.st_n4 = (E - 4 * FS.st_e4) / 4 + 1;
       FS.st_inv2s2 = 0.5 / S.sig_px2;
+    }
+    if (F.cluster && F.obs_sorted) {
+      // tail_cluster.cuh: CTA r of the cluster serves the observed pixels whose position falls into quarter r
+      for (int r = 0; r < 3; ++r) {
+        const double thr = (double)((long long)(r + 1) << (S.log2N2 - 2));
+        int a = 0, b = P.n_obs;                          // first j with (obs_q[j] - q0) * scale >= thr
+        while (a < b) {
+          const int mid = (a + b) >> 1;
+          if ((__ldg(F.obs_q + mid) - FS.q0) * FS.scale >= thr) b = mid; else a = mid + 1;
+        }
+        FS.jcut[r] = a;
+      }
     }
   }
   out->S = S;

@@ -24,8 +24,8 @@ for f, (s, i) in byfile.items():
 src = {}
 import os
 base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'thepayne_b200', 'csrc')
-for f in os.listdir(base): src[f] = open(os.path.join(base, f)).read().split('\n')
-agg.sort(key=lambda a: -a[3])
+for f in [x for x in os.listdir(base) if os.path.isfile(os.path.join(base, x))]: src[f] = open(os.path.join(base, f)).read().split('\n')
+agg.sort(key=lambda a: -a[2 if (len(sys.argv) > 3 and sys.argv[3] == "samples") else 3])
 print('%-14s %4s %6s %6s %6s %6s %6s %6s %6s' % ('file', 'line', 'inst%', 'samp%', 'longsb', 'shrtsb', 'mio', 'bar', 'wait'))
 for a in agg[:top]:
     line = src[a[0]][a[1] - 1].strip()[:72] if a[0] in src and a[1] - 1 < len(src[a[0]]) else ''
