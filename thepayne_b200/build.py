@@ -1,6 +1,6 @@
 """Build libpayne_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-The library is four translation units compiled in parallel (csrc/launchers.h says which kernel family
+The library is six translation units compiled in parallel (csrc/launchers.h says which kernel family
 lives where); objects go to csrc/_build/ (git-ignored) and only the ones whose sources changed are redone.
 """
 import os
@@ -22,7 +22,8 @@ _FAST = _FFT + ['tail_fast.cuh', 'tail_stencil.cuh', 'tail_general.cuh']
 UNITS = {
     'payne_b200.cu': ['mlp_simt.cuh', 'mlp_tc_types.h'] + _FAST + ['launchers.h', 'phot.cuh', 'continuum.cuh', 'tail_lsf.cuh'],
     'gemm_tu.cu': _GEMM + ['mlp_tc_types.h', 'launchers.h'],
-    'tail_fast_tu.cu': _FAST + ['launchers.h'],
+    'tail_fast_tu.cu': _FAST + ['launchers.h', 'tail_fast_tu.inl'],
+    'tail_fast_poly_tu.cu': _FAST + ['launchers.h', 'tail_fast_tu.inl'],
     'tail_cluster_tu.cu': _FAST + ['tail_cluster.cuh', 'launchers.h'],
     'tail_general_tu.cu': _FFT + ['tail_general.cuh', 'tail_lsf.cuh', 'continuum.cuh', 'launchers.h'],
 }
@@ -43,10 +44,11 @@ def _deps(unit):
 # Development switch: PAYNE_FAST_ONLY=14 compiles the fast tail for that transform size only (every other
 # size then reports "unsupported"); the object gets its own name so a full build never picks it up.
 FAST_ONLY = os.environ.get('PAYNE_FAST_ONLY', '')
+_FAST_UNITS = ('tail_fast_tu.cu', 'tail_fast_poly_tu.cu')
 
 
 def _obj(unit):
-    tag = ('_only' + FAST_ONLY) if (FAST_ONLY and unit == 'tail_fast_tu.cu') else ''
+    tag = ('_only' + FAST_ONLY) if (FAST_ONLY and unit in _FAST_UNITS) else ''
     return os.path.join(OBJ, unit[:-3] + tag + '.o')
 
 
@@ -69,7 +71,7 @@ def needs_build():
     if not os.path.exists(OUT) or _flavor() != ('only' + FAST_ONLY if FAST_ONLY else 'full'):
         return True
     t = os.path.getmtime(OUT)
-    if FAST_ONLY and (_stale('tail_fast_tu.cu') or os.path.getmtime(_obj('tail_fast_tu.cu')) > t):
+    if FAST_ONLY and any(_stale(u) or os.path.getmtime(_obj(u)) > t for u in _FAST_UNITS):
         return True
     return any(os.path.getmtime(d) > t for u in UNITS for d in _deps(u))
 
@@ -81,7 +83,7 @@ def _compile(unit, verbose):
            '-Xcompiler', '-fPIC', '-c', '-o', _obj(unit), os.path.join(CSRC, unit)]
     if verbose:
         cmd[1:1] = ['-Xptxas', '-v']
-    if FAST_ONLY and unit == 'tail_fast_tu.cu':
+    if FAST_ONLY and unit in _FAST_UNITS:
         cmd[1:1] = ['-DPAYNE_FAST_ONLY=' + FAST_ONLY]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return unit, r

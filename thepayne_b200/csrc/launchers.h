@@ -37,8 +37,14 @@ int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& 
 // ---- tail_fast_tu.cu: fused tail on log-uniform grids (tail_fast.cuh)
 // sets the dynamic shared-memory opt-in of tail_fast_kernel<l2> on the current device and reports the
 // resident CTAs per SM; false when the kernel does not exist for l2 or the query fails
+// (two instantiations per size, in two translation units: without / with continuum polynomial or model output
+// in the final pass; the probe covers both and reports the smaller occupancy)
 bool probe_tail_fast(int l2, size_t smem_bytes, int* ctas_per_sm);
-int launch_tail_fast(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+int launch_tail_fast(int l2, bool poly, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+bool probe_tail_fast_plain(int l2, size_t smem_bytes, int* ctas_per_sm);
+bool probe_tail_fast_poly(int l2, size_t smem_bytes, int* ctas_per_sm);
+int launch_tail_fast_plain(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+int launch_tail_fast_poly(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
 int launch_tail_setup(int nb, cudaStream_t st, const TailParams& T, const FastGrid& F);
 
 // ---- tail_cluster_tu.cu: the same tail with one transform spread over a cluster of four CTAs (tail_cluster.cuh;

@@ -461,6 +461,10 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
         int occ = 0, ncl = 0;
         if (payne::probe_tail_cluster(l2, base + win, &occ, &ncl) && ncl >= 1) {
           c->use_cluster = 1;
+          // default: 65536-sample transforms only.  Measured on B200 (4096 points): N1 = 65536 (C4) tail 8.0 ms
+          // single-CTA split kernel vs 5.3 ms cluster; N1 = 32768 2.26 ms single CTA (whole transform in 128 KB)
+          // vs 3.13 ms cluster -- there the twelve cluster barriers per point outweigh the occupancy.
+          c->allow_cluster = (l2 >= 16) || (cenv && cenv[0] == '1');
           c->cluster_smem = base + win;
           c->cluster_win_floats = (int)(win / 4);
           c->cluster_n = ncl;
@@ -816,7 +820,8 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
           return fail(PAYNE_E_CUDA, "tail launch");
       } else if (fast_tail && is_depth) {
         const int grid = std::min(c->tail_grid_fast, nb);
-        if (payne::launch_tail_fast(T.log2N1, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
+        const bool poly = T.n_poly != 0 || T.model_out != nullptr;
+        if (payne::launch_tail_fast(T.log2N1, poly, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
       } else {
         if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
         const int grid = std::min(c->tail_grid, nb);

@@ -187,6 +187,39 @@ __device__ __forceinline__ double chebval_dev(double x, const double* c, int nc)
   return c0 + c1 * x;
 }
 
+// The same for four abscissae at once (identical operations per abscissa, coefficient loads shared, four
+// independent dependency chains instead of one).
+__device__ __forceinline__ void chebval_dev4(const double (&x)[4], const double* c, int nc, double (&out)[4]) {
+  if (nc == 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = c[0];
+    return;
+  }
+  if (nc == 2) {
+    const double a = c[0], b = c[1];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = a + b * x[u];
+    return;
+  }
+  double c0[4], c1[4];
+  {
+    const double a = c[nc - 2], b = c[nc - 1];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c0[u] = a; c1[u] = b; }
+  }
+  for (int i = 3; i <= nc; ++i) {
+    const double ci = c[nc - i];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double tmp = c0[u];
+      c0[u] = ci - c1[u];
+      c1[u] = tmp + c1[u] * (2.0 * x[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[u] = c0[u] + c1[u] * x[u];
+}
+
 __device__ __forceinline__ float depth_of(float v, bool is_depth, bool fill_nan) {
   if (fill_nan && v != v) return 0.f;   // nan_to_num(nan=1.0) (smoothing.py:138) in depth space
   return is_depth ? v : v - 1.f;

@@ -128,6 +128,8 @@ __device__ __forceinline__ void cross_dif_regrid(uint32_t zb, unsigned rank, con
 #pragma unroll 2
   for (int i = 0; i < NB; ++i) {
     const int g = g0 + kNT * i;
+    // W_M^{g c}, M = 4Q: requested first, they arrive under the row loads
+    const float2 w1 = tw_load<LOG2MQ + 2>(tw, g), w2 = tw_load<LOG2MQ + 2>(tw, 2 * g), w3 = tw_load<LOG2MQ + 2>(tw, 3 * g);
     float2 v[kCluster];
     {
       const float* src = row + j;
@@ -156,9 +158,9 @@ __device__ __forceinline__ void cross_dif_regrid(uint32_t zb, unsigned rank, con
     j += ij;
     if (rem >= den) { rem -= den; ++j; }
     dft4<false>(v);
-    v[1] = cmul(v[1], tw_load<LOG2MQ + 2>(tw, g));           // W_M^{g c}, M = 4Q
-    v[2] = cmul(v[2], tw_load<LOG2MQ + 2>(tw, 2 * g));
-    v[3] = cmul(v[3], tw_load<LOG2MQ + 2>(tw, 3 * g));
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
     const uint32_t off = 8u * (unsigned)swz(g);
 #pragma unroll
     for (int q = 0; q < kCluster; ++q) stc2(rb[q] + off, v[q]);
@@ -177,12 +179,13 @@ __device__ __forceinline__ void cross_dit(uint32_t zb, unsigned rank, const TwTa
   for (int i = 0; i < NB; ++i) {
     const int g = (int)rank * JW + tid + kNT * i;
     const uint32_t off = 8u * (unsigned)swz(g);
+    const float2 w1 = tw_load<LOG2MQ + 2>(tw, g), w2 = tw_load<LOG2MQ + 2>(tw, 2 * g), w3 = tw_load<LOG2MQ + 2>(tw, 3 * g);
     float2 v[kCluster];
 #pragma unroll
     for (int q = 0; q < kCluster; ++q) v[q] = ldc2(rb[q] + off);
-    v[1] = cmulc(v[1], tw_load<LOG2MQ + 2>(tw, g));
-    v[2] = cmulc(v[2], tw_load<LOG2MQ + 2>(tw, 2 * g));
-    v[3] = cmulc(v[3], tw_load<LOG2MQ + 2>(tw, 3 * g));
+    v[1] = cmulc(v[1], w1);
+    v[2] = cmulc(v[2], w2);
+    v[3] = cmulc(v[3], w3);
     dft4<true>(v);
 #pragma unroll
     for (int q = 0; q < kCluster; ++q) stc2(rb[q] + off, v[q]);
@@ -313,10 +316,12 @@ __device__ __forceinline__ double final_pass_part(const TailParams& P, const Fas
       double x[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) x[u] = (P.n_poly && ((minem >> u) & 1u)) ? __ldcg(P.obs_x + j0 + u * kNT) : 0.0;
+      double cv[U];
+      if (P.n_poly) chebval_dev4(x, S.poly, P.n_poly, cv);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         double m = ((okm >> u) & 1u) ? 1.0 + (double)d[u] : nan;
-        if (P.n_poly) m *= chebval_dev(x[u], S.poly, P.n_poly);
+        if (P.n_poly) m *= cv[u];
         if ((minem >> u) & 1u) {
           if (P.model_out) P.model_out[(long long)p * P.n_obs + j0 + u * kNT] = m;
           const double r = fma(m, is[u], -ot[u]);
@@ -433,7 +438,8 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
         fft_forward(z, log2N2 - 1, plan, twr, tid, kNT);
         filter_pairs(z, log2N2 - 1, plan, twr, H, tid, kNT);
         fft_inverse(z, log2N2 - 1, plan, twr, tid, kNT);
-        acc = final_pass(P, F, S, FS, zs, tid, p, N2);
+        acc = (P.n_poly == 0 && P.model_out == nullptr) ? final_pass<false>(P, F, S, FS, zs, tid, p, N2)
+                                                        : final_pass<true>(P, F, S, FS, zs, tid, p, N2);
       }
     } else {
       // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289); pixels split evenly

@@ -44,20 +44,27 @@ struct FastGrid {
   void* points;                       // [slab] FastPoint, written by tail_setup_kernel
   int win_floats;                     // shared-memory window for the rotation-kernel table (floats; 4 per table interval)
   float* scratch;                     // [grid, N1/2] second half of split transforms (N1 = 65536)
+  TwConst twc;
+  // (behind twc: the constant-bank offsets of the fields above are what the single-CTA kernel was tuned with)
   int obs_sorted;                     // observed wavelengths are non-decreasing (cluster tail: pixel ranges per CTA)
   int cluster;                        // the cluster tail (tail_cluster.cuh) is in use: tail_setup fills FastSetup::jcut
-  TwConst twc;
 };
 
 struct FastSetup {
   int s_incj, s_incr, s_den, s_num;   // stage 2: num = nM-1, den = N2-1, inc for pairs (2*256*num)
   float s_invden;
   int st_R;                           // > 0: stage 2 is the real-space stencil of tail_stencil.cuh, half-width R
-  int st_e4, st_n4;                   // first coefficient step (in units of 4) and number of 4-step groups
-  double st_inv2s2;                   // 1 / (2 sigma_px^2)
+  union {
+    struct {
+      int st_e4, st_n4;               // first coefficient step (in units of 4) and number of 4-step groups
+      double st_inv2s2;               // 1 / (2 sigma_px^2)
+    };
+    // cluster tail (contexts that have it never take the stencil, st_R = 0): first observed pixel at or beyond
+    // sample (r+1) N2/4 (sorted pixels).  Shares the stencil's bytes: the record sits in static shared memory
+    // and every 16 bytes of it come out of the rotation-table window.
+    int jcut[3];
+  };
   double q0, scale;                   // final: p = (obs_q - q0) * scale
-  int jcut[3];                        // cluster tail: first observed pixel at or beyond sample (r+1) N2/4 (sorted pixels)
-  int pad_;
 };
 
 // Per-point setup, computed by tail_setup_kernel (one thread per point) ahead of the tail so that
@@ -198,8 +205,66 @@ __device__ __forceinline__ void regrid_back(float* row, const ZV& zv, const Fast
   }
 }
 
-// observed pixels, continuum, residuals; returns this thread's partial chi2
+// Observed pixels with a continuum polynomial and / or model output (m = (1 + d) chebval(x), r = m / sigma -
+// flux / sigma; fitutils.py:11-20, likelihood.py:95-97): four pixels per trip like the plain path, loads grouped
+// (positions -> samples -> depth; then the per-pixel constants -> Clenshaw on four abscissae at once ->
+// residuals).  It lives in its own instantiation of the kernel (POLY = true): the plain path sits at its 80-register
+// cap and any code beside it changes its allocation (measured: +0.5 % with this loop behind a call).
 template <class ZV>
+__device__ __forceinline__ double final_pass_poly(const TailParams& P, const FastGrid& F, const PointSetup& S,
+                                                  const FastSetup& FS, const ZV& zv, int tid, int p, int N2) {
+  const double nan = CUDART_NAN;
+  const double pmax = (double)(N2 - 1);
+  const float hdu = S.hdu;
+  const double q0 = FS.q0, scale = FS.scale;
+  double acc = 0.0;
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int j0 = tid; j0 < P.n_obs; j0 += U * kNT) {
+    float d[U];
+    unsigned okm = 0;
+    {
+      double q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) q[u] = (j0 + u * kNT < P.n_obs) ? __ldcg(F.obs_q + j0 + u * kNT) : -1.0;
+      float g0[U], g1[U], dl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double pp = (q[u] - q0) * scale;
+        const bool ok = (pp >= 0.0 && pp <= pmax);         // smoothing.py:289 left/right = nan
+        const int k = ok ? min((int)pp, N2 - 2) : 0;
+        okm |= (unsigned)ok << u;
+        dl[u] = (float)(pp - (double)k);
+        g0[u] = zv.ld(k); g1[u] = zv.ld(k + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) d[u] = fmaf(interp_w(dl[u], hdu), g1[u] - g0[u], g0[u]);
+    }
+    double is[U], ot[U], x[U], cv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool in = j0 + u * kNT < P.n_obs;
+      is[u] = in ? __ldcg(P.obs_inv_s + j0 + u * kNT) : 0.0;
+      ot[u] = in ? __ldcg(P.obs_ot + j0 + u * kNT) : 0.0;
+      x[u] = (in && P.n_poly) ? __ldcg(P.obs_x + j0 + u * kNT) : 0.0;
+    }
+    if (P.n_poly) chebval_dev4(x, S.poly, P.n_poly, cv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double m = ((okm >> u) & 1u) ? 1.0 + (double)d[u] : nan;
+      if (P.n_poly) m *= cv[u];
+      if (j0 + u * kNT < P.n_obs) {
+        if (P.model_out) P.model_out[(long long)p * P.n_obs + j0 + u * kNT] = m;
+        const double r = fma(m, is[u], -ot[u]);
+        acc = fma(r, r, acc);
+      }
+    }
+  }
+  return acc;
+}
+
+// observed pixels, continuum, residuals; returns this thread's partial chi2
+template <bool POLY, class ZV>
 __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid& F, const PointSetup& S,
                                              const FastSetup& FS, const ZV& zv, int tid, int p, int N2) {
   const double nan = CUDART_NAN;
@@ -207,7 +272,7 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
   const float hdu = S.hdu;
   const double q0 = FS.q0, scale = FS.scale;
   double acc = 0.0;
-  if (P.n_poly == 0 && P.model_out == nullptr) {
+  if (!POLY) {
     // four pixels per trip: the twelve per-pixel constants are requested together, then the eight
     // shared-memory samples, then the arithmetic (the phase is latency-bound at 24 warps per SM)
     constexpr int U = 4;
@@ -241,21 +306,7 @@ __device__ __forceinline__ double final_pass(const TailParams& P, const FastGrid
       }
     }
   } else {
-    for (int j = tid; j < P.n_obs; j += kNT) {
-      const double pp = (__ldg(F.obs_q + j) - q0) * scale;
-      double m;
-      if (!(pp >= 0.0 && pp <= pmax)) m = nan;
-      else {
-        const int k = min((int)pp, N2 - 2);
-        const float dl = (float)(pp - (double)k);
-        const float g0 = zv.ld(k), g1 = zv.ld(k + 1);
-        m = 1.0 + (double)fmaf(interp_w(dl, hdu), g1 - g0, g0);
-      }
-      if (P.n_poly) m *= chebval_dev(__ldg(P.obs_x + j), S.poly, P.n_poly);
-      if (P.model_out) P.model_out[(long long)p * P.n_obs + j] = m;
-      const double r = m * __ldg(P.obs_inv_s + j) - __ldg(P.obs_ot + j);
-      acc += r * r;
-    }
+    acc = final_pass_poly(P, F, S, FS, zv, tid, p, N2);
   }
   return acc;
 }
@@ -276,7 +327,8 @@ static __device__ __noinline__ void discard_lines(const float* row, int n, int t
 
 // LOG2N1 <= 15: the whole transform sits in shared memory (3 CTAs/SM up to 2^14).
 // LOG2N1 == 16: split transform, half in shared memory (128 KB), half in the scratch line.
-template <int LOG2N1>
+// POLY: continuum polynomial and / or model output in the final pass (the host picks the instantiation).
+template <int LOG2N1, bool POLY>
 __global__ void __launch_bounds__(kNT, LOG2N1 <= 14 ? PAYNE_TAIL_MINB : 1)
 tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ FastGrid F) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -364,7 +416,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
           stage_regrid(S, row, zp, tid, N2, FS.s_num, FS.s_den, i0, FS.s_invden, F.c_native, FS.s_incj, FS.s_incr);
           __syncthreads();
           ct_convolve_split<LOG2MH>(z, reinterpret_cast<float2*>(gline), tw, F.twc, H, tid);
-          acc = final_pass(P, F, S, FS, zp, tid, p, N2);
+          acc = final_pass<POLY>(P, F, S, FS, zp, tid, p, N2);
         }
       } else {
         constexpr int LA = LOG2N1 > 15 ? 15 : LOG2N1;       // largest all-in-smem transform
@@ -384,7 +436,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
             ct_convolve_regrid<(LA >= 10 ? LA - 2 : 8)>(z, tw, F.twc, H, tid, row + i0, FS.s_num, FS.s_den,
                                                          FS.s_invden, F.c_native, S.clean != 0);
         }
-        if (!(P.debug_skip & 16)) acc = final_pass(P, F, S, FS, zs, tid, p, N2);
+        if (!(P.debug_skip & 16)) acc = final_pass<POLY>(P, F, S, FS, zs, tid, p, N2);
       }
     } else {
       // ---------------- no instrumental profile: plain np.interp (predictspec.py:288-289)
@@ -461,6 +513,7 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
       FS.st_n4 = (E - 4 * FS.st_e4) / 4 + 1;
       FS.st_inv2s2 = 0.5 / S.sig_px2;
     }
+    if (F.cluster) FS.st_R = 0;
     if (F.cluster && F.obs_sorted) {
       // tail_cluster.cuh: CTA r of the cluster serves the observed pixels whose position falls into quarter r
       for (int r = 0; r < 3; ++r) {

@@ -1,44 +1,3 @@
-// Translation unit of the fast fused tail (tail_fast.cuh); see launchers.h.
-#include "launchers.h"
-
-namespace payne {
-
-// PAYNE_FAST_ONLY=<log2 N1> (development builds, thepayne_b200/build.py): compile that one transform size only
-#ifdef PAYNE_FAST_ONLY
-#define PAYNE_FAST_SIZES(X) X(PAYNE_FAST_ONLY)
-#else
-#define PAYNE_FAST_SIZES(X) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
-#endif
-
-bool probe_tail_fast(int l2, size_t bytes, int* occ) {
-  cudaError_t e1 = cudaErrorInvalidValue, e2 = cudaErrorInvalidValue;
-  switch (l2) {
-#define X(L)                                                                                                   \
-    case L:                                                                                                    \
-      e1 = cudaFuncSetAttribute(tail_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
-      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, tail_fast_kernel<L>, kNT, bytes);                \
-      break;
-    PAYNE_FAST_SIZES(X)
-#undef X
-    default: break;
-  }
-  if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); return false; }
-  return true;
-}
-
-int launch_tail_fast(int l2, int grid, size_t smem, cudaStream_t st, const TailParams& T, const FastGrid& F) {
-  switch (l2) {
-#define X(L) case L: tail_fast_kernel<L><<<grid, kNT, smem, st>>>(T, F); break;
-    PAYNE_FAST_SIZES(X)
-#undef X
-    default: return PAYNE_E_UNSUPPORTED;
-  }
-  return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
-}
-
-int launch_tail_setup(int nb, cudaStream_t st, const TailParams& T, const FastGrid& F) {
-  tail_setup_kernel<0><<<(nb + 63) / 64, 64, 0, st>>>(T, F);
-  return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
-}
-
-}  // namespace payne
+// Translation unit of the fast fused tail without continuum polynomial / model output (tail_fast_tu.inl).
+#define PAYNE_TU_POLY 0
+#include "tail_fast_tu.inl"
