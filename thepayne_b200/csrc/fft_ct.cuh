@@ -319,8 +319,9 @@ __device__ __forceinline__ void ct_pass0_regrid(float2* z, const TwTab& tw, cons
   }
 }
 
+// inverse transform = contiguous pass + strided passes n-1 .. 1 (`mid`), then strided pass 0 (`last`)
 template <int LOG2M>
-__device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+__device__ __forceinline__ void ct_fft_inverse_mid(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
   using P = CtPlan<LOG2M>;
   constexpr bool WL = CtLast<LOG2M>::kWarpLocal;
   ct_contiguous16<LOG2M, true>(z, tid);
@@ -328,7 +329,64 @@ __device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const
   if constexpr (P::n > 3) { ct_strided_pass<LOG2M, 3, true>(z, tw, tc, tid); __syncthreads(); }
   if constexpr (P::n > 2) { ct_strided_pass<LOG2M, 2, true>(z, tw, tc, tid); __syncthreads(); }
   if constexpr (P::n > 1) { ct_strided_pass<LOG2M, 1, true>(z, tw, tc, tid); __syncthreads(); }
+}
+template <int LOG2M>
+__device__ __forceinline__ void ct_fft_inverse_last(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  using P = CtPlan<LOG2M>;
   if constexpr (P::n > 0) { ct_strided_pass<LOG2M, 0, true>(z, tw, tc, tid); __syncthreads(); }
+}
+template <int LOG2M>
+__device__ __forceinline__ void ct_fft_inverse(float2* z, const TwTab& tw, const TwConst& tc, int tid) {
+  ct_fft_inverse_mid<LOG2M>(z, tw, tc, tid);
+  ct_fft_inverse_last<LOG2M>(z, tw, tc, tid);
+}
+
+// The passes of a convolution that do not depend on the filter (the fused first pass, the other forward passes,
+// all inverse passes) as ONE copy of code per size, called from the rotation and the instrumental stage alike.
+// Inlined into both they made the point loop of the fused tail ~15 k instructions (240 KB), more than the
+// instruction cache holds with three CTAs per SM in different phases, and the kernel spilled (324 bytes at the
+// 80-register cap; 0 with the passes in functions of their own, each with its own register allocation):
+// C2 tail 0.736 -> 0.699 ms, measured A/B on one box.
+// The transform buffer is the base of the dynamic shared memory (re-declared inside so that the accesses stay
+// LDS / STS); the first-pass constants come from a __constant__ copy (one per translation unit, set by
+// ct_set_twconst at context creation) so that they stay constant-bank operands.
+#ifndef PAYNE_SHARED_PASSES
+#define PAYNE_SHARED_PASSES 1
+#endif
+#ifndef PAYNE_SHARE_PASS0
+#define PAYNE_SHARE_PASS0 0
+#endif
+#ifndef PAYNE_SHARE_INV0
+#define PAYNE_SHARE_INV0 0
+#endif
+static __constant__ TwConst g_twc;
+static inline cudaError_t ct_set_twconst(const TwConst& h) { return cudaMemcpyToSymbol(g_twc, &h, sizeof(TwConst)); }
+
+template <int LOG2M>
+static __device__ __noinline__ void ct_fwd_mid_shared(const TwTab tw, int tid) {       // forward passes 1.. + contiguous
+  extern __shared__ __align__(16) unsigned char ct_dyn_smem[];
+  ct_fft_forward_rest<LOG2M>(reinterpret_cast<float2*>(ct_dyn_smem), tw, g_twc, tid);
+}
+template <int LOG2M>
+static __device__ __noinline__ void ct_fwd_all_shared(const TwTab tw, int tid) {       // whole forward transform
+  extern __shared__ __align__(16) unsigned char ct_dyn_smem[];
+  ct_fft_forward<LOG2M>(reinterpret_cast<float2*>(ct_dyn_smem), tw, g_twc, tid);
+}
+template <int LOG2M>
+static __device__ __noinline__ void ct_inv_mid_shared(const TwTab tw, int tid) {       // inverse contiguous + passes .. 1
+  extern __shared__ __align__(16) unsigned char ct_dyn_smem[];
+  ct_fft_inverse_mid<LOG2M>(reinterpret_cast<float2*>(ct_dyn_smem), tw, g_twc, tid);
+}
+template <int LOG2M>
+static __device__ __noinline__ void ct_inv_all_shared(const TwTab tw, int tid) {       // whole inverse transform
+  extern __shared__ __align__(16) unsigned char ct_dyn_smem[];
+  ct_fft_inverse<LOG2M>(reinterpret_cast<float2*>(ct_dyn_smem), tw, g_twc, tid);
+}
+template <int LOG2M, bool CLEAN>
+static __device__ __noinline__ void ct_pass0_regrid_shared(const TwTab tw, int tid, const float* row, int num, int den,
+                                                           float invden, float c) {
+  extern __shared__ __align__(16) unsigned char ct_dyn_smem[];
+  ct_pass0_regrid<LOG2M, CLEAN>(reinterpret_cast<float2*>(ct_dyn_smem), tw, g_twc, tid, row, num, den, invden, c);
 }
 
 // Filter stage on digit-reversed storage; H(k), k in [0, M], includes the 1/M of the inverse.
@@ -493,11 +551,30 @@ template <int LOG2M, class HF>
 __device__ __forceinline__ void ct_convolve_regrid(float2* z, const TwTab& tw, const TwConst& tc, const HF& H, int tid,
                                                    const float* row, int num, int den, float invden, float c,
                                                    bool clean) {
+#if PAYNE_SHARED_PASSES
+  // z is the base of the dynamic shared memory (tail_fast.cuh) and tc the context's copy of g_twc
+#if PAYNE_SHARE_PASS0
+  if (clean) ct_pass0_regrid_shared<LOG2M, true>(tw, tid, row, num, den, invden, c);
+  else ct_pass0_regrid_shared<LOG2M, false>(tw, tid, row, num, den, invden, c);
+#else
+  if (clean) ct_pass0_regrid<LOG2M, true>(z, tw, tc, tid, row, num, den, invden, c);
+  else ct_pass0_regrid<LOG2M, false>(z, tw, tc, tid, row, num, den, invden, c);
+#endif
+  ct_fwd_mid_shared<LOG2M>(tw, tid);
+  ct_filter_pairs<LOG2M>(z, tw, H, tid);
+#if PAYNE_SHARE_INV0
+  ct_inv_all_shared<LOG2M>(tw, tid);
+#else
+  ct_inv_mid_shared<LOG2M>(tw, tid);
+  ct_fft_inverse_last<LOG2M>(z, tw, tc, tid);
+#endif
+#else
   if (clean) ct_pass0_regrid<LOG2M, true>(z, tw, tc, tid, row, num, den, invden, c);
   else ct_pass0_regrid<LOG2M, false>(z, tw, tc, tid, row, num, den, invden, c);
   ct_fft_forward_rest<LOG2M>(z, tw, tc, tid);
   ct_filter_pairs<LOG2M>(z, tw, H, tid);
   ct_fft_inverse<LOG2M>(z, tw, tc, tid);
+#endif
 }
 
 template <int LOG2M, class HF>

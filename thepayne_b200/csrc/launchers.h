@@ -41,6 +41,12 @@ int tc_gemm_test_x(const float* dA, int M, int N, int K, int precision, TcActs& 
 // in the final pass; the probe covers both and reports the smaller occupancy)
 bool probe_tail_fast(int l2, size_t smem_bytes, int* ctas_per_sm);
 int launch_tail_fast(int l2, bool poly, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);
+// copies the first-pass constants into the translation units' __constant__ memory on the current device
+// (call once per context, before the first launch)
+int init_tail_fast(const TwConst& tc);
+int init_tail_fast_plain(const TwConst& tc);
+int init_tail_fast_poly(const TwConst& tc);
+int init_tail_cluster(const TwConst& tc);
 bool probe_tail_fast_plain(int l2, size_t smem_bytes, int* ctas_per_sm);
 bool probe_tail_fast_poly(int l2, size_t smem_bytes, int* ctas_per_sm);
 int launch_tail_fast_plain(int l2, int grid, size_t smem_bytes, cudaStream_t st, const TailParams& T, const FastGrid& F);

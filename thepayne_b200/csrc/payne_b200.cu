@@ -416,6 +416,8 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
         }
   }
   if (c->use_fast) {
+    if (payne::init_tail_fast(c->fast.twc) || payne::init_tail_cluster(c->fast.twc))
+      return fail(PAYNE_E_CUDA, "tail constants");
     // Shared memory left over next to the transform buffer holds the slice of the rotation-kernel
     // table a point actually uses (its lookups are scattered across lanes; from shared memory each
     // costs one wavefront instead of one per touched line).  Take the largest slice that does not

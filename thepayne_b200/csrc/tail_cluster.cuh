@@ -242,7 +242,7 @@ __device__ __forceinline__ void convolve_regrid(float2* z, uint32_t zb, unsigned
   CL_PROF(slot + 0);
   cluster_sync();
   CL_PROF(slot + 1);
-  ct_fft_forward<LOG2MQ>(z, tw, tc, tid);
+  ct_fwd_all_shared<LOG2MQ>(tw, tid);                    // z is the base of the dynamic shared memory
   CL_PROF(slot + 2);
   cluster_sync();                                       // the partner class is transformed too
   CL_PROF(slot + 3);
@@ -251,7 +251,7 @@ __device__ __forceinline__ void convolve_regrid(float2* z, uint32_t zb, unsigned
   CL_PROF(slot + 4);
   cluster_sync();
   CL_PROF(slot + 5);
-  ct_fft_inverse<LOG2MQ>(z, tw, tc, tid);
+  ct_inv_all_shared<LOG2MQ>(tw, tid);
   CL_PROF(slot + 6);
   cluster_sync();
   CL_PROF(slot + 7);

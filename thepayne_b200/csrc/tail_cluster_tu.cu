@@ -28,6 +28,8 @@ cudaLaunchConfig_t cluster_config(K, int grid, size_t smem, cudaStream_t st, cud
 }
 }  // namespace
 
+int init_tail_cluster(const TwConst& tc) { return ct_set_twconst(tc) == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA; }
+
 bool probe_tail_cluster(int l2, size_t bytes, int* ctas_per_sm, int* max_clusters) {
   cudaError_t e1 = cudaErrorInvalidValue, e2 = cudaErrorInvalidValue, e3 = cudaErrorInvalidValue;
   cudaLaunchAttribute attr;

@@ -34,6 +34,9 @@ bool PAYNE_TU_NAME(probe_tail_fast)(int l2, size_t bytes, int* occ) {
   return true;
 }
 
+// first-pass constants of the shared transform passes (fft_ct.cuh g_twc) on the current device
+int PAYNE_TU_NAME(init_tail_fast)(const TwConst& tc) { return ct_set_twconst(tc) == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA; }
+
 int PAYNE_TU_NAME(launch_tail_fast)(int l2, int grid, size_t smem, cudaStream_t st, const TailParams& T, const FastGrid& F) {
   switch (l2) {
 #define X(L) case L: tail_fast_kernel<L, PAYNE_TU_POLY != 0><<<grid, kNT, smem, st>>>(T, F); break;
@@ -50,6 +53,11 @@ bool probe_tail_fast(int l2, size_t bytes, int* occ) {
   if (!probe_tail_fast_plain(l2, bytes, &o1) || !probe_tail_fast_poly(l2, bytes, &o2)) return false;
   *occ = o1 < o2 ? o1 : o2;
   return true;
+}
+
+int init_tail_fast(const TwConst& tc) {
+  const int a = init_tail_fast_plain(tc), b = init_tail_fast_poly(tc);
+  return a ? a : b;
 }
 
 int launch_tail_fast(int l2, bool poly, int grid, size_t smem, cudaStream_t st, const TailParams& T, const FastGrid& F) {
