@@ -174,6 +174,7 @@ struct PayneCtx {
   // host staging
   long long stage_cap = 0, stage_ld = 0;
   double *theta_pin = nullptr, *lnl_pin = nullptr, *theta_stage = nullptr, *lnl_stage = nullptr;
+  double* lnl_map = nullptr;       // device view of lnl_pin (zero-copy result: the tail writes lnL straight to the host)
   // device allocations to free
   std::vector<void*> owned;
   // timing
@@ -439,6 +440,16 @@ int build_tail(PayneCtx* c, const PayneSpecNet* s, const PayneObs* obs) {
     c->fast.win_floats = (int)(win / 4);
     probe(c->fast_smem, &occf);
     c->tail_grid_fast = occf * c->sm_count;
+    {
+      const char* denv = getenv("PAYNE_TAIL_DYNAMIC");       // "0": static round robin of points over the CTAs
+      if (!(denv && denv[0] == '0')) {
+        int* wc = nullptr;
+        CU_TRY(cudaMalloc((void**)&wc, sizeof(int)));
+        CU_TRY(cudaMemset(wc, 0, sizeof(int)));
+        c->owned.push_back(wc);
+        c->fast.work_counter = wc;
+      }
+    }
     if (c->use_fast && l2 >= 16) {
       float* sc = nullptr;
       CU_TRY(cudaMalloc((void**)&sc, (size_t)c->tail_grid_fast * (N1 / 2) * sizeof(float)));
@@ -775,6 +786,8 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         // per-point setup depends only on theta: fork it beside the emulator GEMMs, join before the tail
         CU_TRY(cudaEventRecord(c->ev_fork, st));
         CU_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        c->fast.work_start = (c->use_cluster && c->allow_cluster) ? (int)std::min<long long>(c->cluster_n, nb)
+                                                                  : std::min(c->tail_grid_fast, nb);
         if (payne::launch_tail_setup(nb, c->side, T, c->fast)) return fail(PAYNE_E_CUDA, "tail_setup launch");
         CU_TRY(cudaEventRecord(c->ev_join, c->side));
         c->launches++;
@@ -933,20 +946,27 @@ int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, in
     if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
     if (c->theta_stage) cudaFree(c->theta_stage);
     if (c->lnl_stage) cudaFree(c->lnl_stage);
-    c->theta_pin = c->lnl_pin = c->theta_stage = c->lnl_stage = nullptr; c->stage_cap = 0;
+    c->theta_pin = c->lnl_pin = c->theta_stage = c->lnl_stage = nullptr; c->lnl_map = nullptr; c->stage_cap = 0;
     CU_TRY(cudaMallocHost((void**)&c->theta_pin, (size_t)B * ld * sizeof(double)));
     CU_TRY(cudaMallocHost((void**)&c->lnl_pin, (size_t)B * sizeof(double)));
     CU_TRY(cudaMalloc((void**)&c->theta_stage, (size_t)B * ld * sizeof(double)));
     CU_TRY(cudaMalloc((void**)&c->lnl_stage, (size_t)B * sizeof(double)));
     c->stage_cap = B; c->stage_ld = ld;
+    // 8 bytes per point: the last kernel writes them into the pinned buffer itself (mapped under unified
+    // addressing) instead of a device buffer + a D2H copy behind it (one enqueue and one copy latency per call)
+    void* dp = nullptr;
+    const char* zenv = getenv("PAYNE_ZERO_COPY_LNL");
+    c->lnl_map = (!(zenv && zenv[0] == '0') && cudaHostGetDevicePointer(&dp, c->lnl_pin, 0) == cudaSuccess) ? (double*)dp : nullptr;
+    cudaGetLastError();
   }
   std::memcpy(c->theta_pin, theta_host, (size_t)B * ld * sizeof(double));
   CU_TRY(cudaMemcpyAsync(c->theta_stage, c->theta_pin, (size_t)B * ld * sizeof(double),
                          cudaMemcpyHostToDevice, c->stream));
-  int rc = run_batch(c, c->theta_stage, B, ld, nullptr, nullptr, c->lnl_stage, c->stream);
+  int rc = run_batch(c, c->theta_stage, B, ld, nullptr, nullptr, c->lnl_map ? c->lnl_map : c->lnl_stage, c->stream);
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(c->lnl_pin, c->lnl_stage, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost,
-                         c->stream));
+  if (!c->lnl_map)
+    CU_TRY(cudaMemcpyAsync(c->lnl_pin, c->lnl_stage, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost,
+                           c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   std::memcpy(lnl_host, c->lnl_pin, (size_t)B * sizeof(double));
   return PAYNE_OK;

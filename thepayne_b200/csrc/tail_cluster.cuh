@@ -367,8 +367,20 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
   const FastPoint* points = reinterpret_cast<const FastPoint*>(F.points);
   const ZSmem zs{zf};
 
-  for (int p = (int)cl::cluster_id(); p < P.B; p += (int)cl::n_clusters()) {
+  // Dynamic point scheduling: CTA 0 claims the cluster's next point at the top of a point and posts it into every
+  // CTA's c_next[parity]; the point's last cluster barrier publishes it.  Two slots: CTA 0 may already be posting
+  // point i+1's successor while a slower CTA still reads point i's.
+  __shared__ int c_next[2];
+  int pn, it = 0;
+  for (int p = (int)cl::cluster_id(); p < P.B; p = pn, it ^= 1) {
     float* row = P.flux + (long long)p * P.ldf;
+    if (rank == 0 && tid == 0) {
+      const int v = F.work_counter ? atomicAdd(F.work_counter, 1) : p + (int)cl::n_clusters();
+      const uint32_t a = cl::smem_u32(&c_next[it]);
+#pragma unroll
+      for (unsigned r = 0; r < cl::kCluster; ++r)
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cl::mapa(a, r)), "r"(v) : "memory");
+    }
     if (tid < (int)(sizeof(FastPoint) / 16))
       reinterpret_cast<int4*>(&SP)[tid] = __ldg(reinterpret_cast<const int4*>(points + p) + tid);
     __syncthreads();
@@ -378,7 +390,8 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
           for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
         if (tid == 0 && P.lnl) P.lnl[p] = nan;
       }
-      __syncthreads();
+      cl::cluster_sync();
+      pn = c_next[it];
       continue;
     }
     const int n = P.n;
@@ -475,6 +488,7 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
     }
     cl::cluster_sync();                                  // partial sums landed; nobody reads a transform buffer any more
     CL_PROF(23);
+    pn = c_next[it];
     if (rank == 0 && tid == 0 && P.lnl) {
       double c2 = (cred[0] + cred[1]) + (cred[2] + cred[3]);
       if (P.chi2_sed) c2 += P.chi2_sed[p];

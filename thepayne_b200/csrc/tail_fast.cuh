@@ -48,6 +48,10 @@ struct FastGrid {
   // (behind twc: the constant-bank offsets of the fields above are what the single-CTA kernel was tuned with)
   int obs_sorted;                     // observed wavelengths are non-decreasing (cluster tail: pixel ranges per CTA)
   int cluster;                        // the cluster tail (tail_cluster.cuh) is in use: tail_setup fills FastSetup::jcut
+  // dynamic point scheduling of tail_fast_kernel: CTA b starts with point b and takes further points from this
+  // counter (reset to work_start = the tail's grid size by tail_setup_kernel); null = static round robin
+  int* work_counter;
+  int work_start;
 };
 
 struct FastSetup {
@@ -353,11 +357,19 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   float* win = zf + (kSplit ? N1 / 2 : N1);               // rotation-table window behind the transform buffer
   const FastPoint* points = reinterpret_cast<const FastPoint*>(F.points);
 
-  for (int p = blockIdx.x; p < P.B; p += gridDim.x) {
+  // (lives in red[0], which is dead between the end of one point and the reduction of the next: 16 more bytes of
+  // static shared memory would come out of every point's rotation-table window)
+  int& s_next = *reinterpret_cast<int*>(&red[0]);
+  int pn;
+  for (int p = blockIdx.x; p < P.B; p = pn) {
     float* row = P.flux + (long long)p * P.ldf;
+    // the next point is claimed now (its latency hides under this point) and read after the barrier below; thread 0
+    // writes s_next again only behind this iteration's last barrier
+    if (tid == 0) s_next = F.work_counter ? atomicAdd(F.work_counter, 1) : p + (int)gridDim.x;
     if (tid < (int)(sizeof(FastPoint) / 16))
       reinterpret_cast<int4*>(&SP)[tid] = __ldg(reinterpret_cast<const int4*>(points + p) + tid);
     __syncthreads();
+    pn = s_next;
     if (S.bad) {
       if (P.model_out)
         for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
@@ -489,6 +501,7 @@ tail_setup_kernel(const __grid_constant__ TailParams P, const __grid_constant__ 
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.B) return;
   FastPoint* out = reinterpret_cast<FastPoint*>(F.points) + p;
+  if (p == 0 && F.work_counter) *F.work_counter = F.work_start;
   PointSetup S{};
   FastSetup FS{};
   tail_setup(P, P.theta + (long long)p * P.ld, S);
