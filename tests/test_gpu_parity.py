@@ -376,3 +376,27 @@ def test_legacy_output_layer_on_tensor_cores(name):
     assert np.max(np.abs(fa[fin] - fb[fin]) / np.abs(fb[fin])) <= 2.5e-7
     yo = O.make_net(cfg.spec)(th[:, :cfg.spec.D_in].cpu().numpy())
     assert np.max(np.abs(ya - yo) / np.abs(yo)) <= 5e-7 and np.max(np.abs(yb - yo) / np.abs(yo)) <= 1e-6
+
+
+@pytest.mark.parametrize('name', ['mini_spec', 'c2', 'c4m', 'mini_odd'])
+def test_hidden_stack_launch_is_bit_identical(name):
+    """lin2..lin5 as one cluster launch (csrc/mlp_stack.cuh; clusters of 1 / 4 / 8 CTAs for hidden widths 64 / 256 / 512)
+    against one launch per layer: same ring, same MMAs, same epilogue -> the same bits; three launches fewer per call.
+    Hidden width 100 (mini_odd) does not tile into 64-column CTAs and keeps the per-layer launches."""
+    cfg, g = load_case(name)
+    eng = _engine(cfg, 'parity')
+    th = torch.from_numpy(np.ascontiguousarray(np.concatenate([g['theta'], cfg.draw(150, seed=8)]))).cuda()
+    x = torch.from_numpy(np.ascontiguousarray(cfg.draw(133, seed=9)[:, :eng.D_in])).cuda()
+    out = {}
+    for mode in (1, 0):
+        eng.set('gemm_stack', mode)
+        assert eng.query('gemm_stack') == mode
+        l0 = eng.query('launches')
+        y = eng.ann_eval(x)
+        torch.cuda.synchronize()
+        n = eng.query('launches') - l0
+        out[mode] = (y.cpu().numpy(), eng.lnlike_batch(th).cpu().numpy(), n)
+    assert np.array_equal(out[1][0], out[0][0])
+    assert np.array_equal(out[1][1], out[0][1], equal_nan=True)
+    assert out[0][2] - out[1][2] == (0 if name == 'mini_odd' else 3)
+    eng.close()

@@ -1,5 +1,6 @@
 // Translation unit of the tcgen05 GEMM templates (mlp_tc.cuh); see launchers.h.
 #include "mlp_tc.cuh"
+#include "mlp_stack.cuh"
 #include "launchers.h"
 
 namespace payne {
@@ -22,9 +23,9 @@ int launch_encode_x3(const EncodeParams& E, const double* x, long long ld, const
 int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                     const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
                     float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
-                    TcMapCache* caches, long long out_rows) {
+                    TcMapCache* caches, long long out_rows, TcStackCache* stack_cache) {
   return tc_run_layers(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift, prec, sm_count, st,
-                       launches, caches, out_rows);
+                       launches, caches, out_rows, stack_cache);
 }
 
 int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,

@@ -21,7 +21,7 @@ int launch_encode_x3(const EncodeParams& E, const double* x, long long ld, const
 int tc_run_layers_x(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                     const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
                     float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
-                    TcMapCache* caches, long long out_rows);
+                    TcMapCache* caches, long long out_rows, TcStackCache* stack_cache = nullptr);
 int tc_run_multinet_x(const TcWeights* tcw, float* const* bias, int H, int D_out, int groups, int chunk,
                       TcActs* actA, TcActs* actB, long long rows_per_group, int nb, float* out, long long ldo,
                       float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,

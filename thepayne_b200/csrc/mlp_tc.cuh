@@ -1192,11 +1192,14 @@ inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bi
                                           map_rows);
 }
 
+inline int tc_launch_hidden_stack(const TcWeights* tcw, float* const* bias, int layers, int H, TcActs* a0, TcActs* a1,
+                                  int M, cudaStream_t st, TcStackCache* cache);      // mlp_stack.cuh
+
 template <int MODE>
 inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                               const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
                               float bias_shift, int sm_count, cudaStream_t st, long long* launches,
-                              TcMapCache* caches, long long out_rows) {
+                              TcMapCache* caches, long long out_rows, TcStackCache* stack_cache = nullptr) {
   const long long tot = (long long)nb * dims_out[0];
   const unsigned blocks = (unsigned)((tot + 255) / 256);
   if (h1 == nullptr)
@@ -1211,7 +1214,17 @@ inline int tc_run_layers_mode(const TcWeights* tcw, float* const* bias, const in
   ++*launches;
   TcActs* cur = actA; TcActs* nxt = actB;
   int rc = PAYNE_OK;
-  for (int k = 1; k < 5 && !rc; ++k) {
+  bool stacked = false;
+  if constexpr (MODE == kModeX3) {
+    // lin2 .. lin5 in one launch when they are all H -> H (mlp_stack.cuh); four layers end in actA again
+    bool uniform = true;
+    for (int k = 1; k < 5; ++k) uniform = uniform && dims_in[k] == dims_in[1] && dims_out[k] == dims_in[1];
+    if (uniform && stack_cache && tc_launch_hidden_stack(tcw, bias, 4, dims_in[1], actA, actB, nb, st, stack_cache) == PAYNE_OK) {
+      stacked = true;
+      ++*launches;
+    }
+  }
+  for (int k = 1; k < 5 && !rc && !stacked; ++k) {
     rc = tc_launch<64, MODE, 1>(*cur, dims_in[k], tcw[k], bias[k], nxt->plane[0], nxt->plane[1], nxt->plane[2],
                                 nxt->ld, 0.f, nb, sm_count, st, caches ? caches + k : nullptr, cur->rows);
     ++*launches;
@@ -1312,7 +1325,7 @@ inline int tc_run_scaled_layer(const TcWeights& w, const float* bias, const floa
 inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* dims_in, const int* dims_out,
                          const float* h1, TcActs* actA, TcActs* actB, int nb, float* out, long long ldo,
                          float bias_shift, int prec, int sm_count, cudaStream_t st, long long* launches,
-                         TcMapCache* caches = nullptr, long long out_rows = 0) {
+                         TcMapCache* caches = nullptr, long long out_rows = 0, TcStackCache* stack_cache = nullptr) {
   for (int k = 1; k < 6; ++k)
     if (!tcw[k].plane[0]) return PAYNE_E_UNSUPPORTED;
   // exactness of the leading product sum (header): K * 2^8 * 2^7 <= 2^24 needs K <= 512
@@ -1322,7 +1335,7 @@ inline int tc_run_layers(const TcWeights* tcw, float* const* bias, const int* di
   switch (prec) {
     case PAYNE_PREC_PARITY:
       return tc_run_layers_mode<kModeX3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
-                                         sm_count, st, launches, caches, out_rows);
+                                         sm_count, st, launches, caches, out_rows, stack_cache);
     case PAYNE_PREC_3XTF32:
       return tc_run_layers_mode<kModeT3>(tcw, bias, dims_in, dims_out, h1, actA, actB, nb, out, ldo, bias_shift,
                                          sm_count, st, launches, caches, out_rows);

@@ -38,5 +38,26 @@ struct TcMapCache {
   int variant = -1;
 };
 
+// The hidden-layer stack as one launch (mlp_stack.cuh): maps of the two ping-pong activation buffers and of
+// up to four layers' weight planes; arguments; and the cache of the encoded maps.
+constexpr int kStackMaxLayers = 4;
+struct TcStackMaps {
+  CUtensorMap a[2][3];
+  CUtensorMap b[kStackMaxLayers][3];
+};
+struct TcStackArgs {
+  const float* bias[kStackMaxLayers];
+  const float* wscale[kStackMaxLayers];   // per output column power-of-two scale of the weight slices
+  void* plane[2][3];                      // bf16 planes of the two buffers; layer l reads (first + l) & 1, writes the other
+  long long ld;                           // plane pitch in elements
+  int M, H, layers, first;
+};
+struct TcStackCache {
+  TcStackMaps maps;
+  const void* a0 = nullptr; const void* a1 = nullptr; const void* w0 = nullptr;
+  long long rows = 0, lda = 0;
+  int H = 0, layers = 0;
+  bool valid = false;
+};
 
 }  // namespace payne

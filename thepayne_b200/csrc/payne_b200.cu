@@ -126,6 +126,8 @@ struct PayneCtx {
   int n_groups = 1, chunk = 0;
   long long rows_per_group = 0;    // rows of one group's block in the activation planes (workspace)
   payne::TcMapCache mapc[6];       // tensor maps per layer, valid while the workspace stays put
+  payne::TcStackCache stackc;      // ... and of the hidden-layer stack (one launch for lin2..lin5)
+  bool use_stack = true;           // PAYNE_GEMM_STACK=0 / payne_ctx_set("gemm_stack", 0): one launch per hidden layer
   cudaStream_t side = nullptr;     // per-point tail setup runs here, beside the emulator GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_done = nullptr;   // end of the last call that used the workspace
@@ -747,7 +749,7 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
     int rc = tc_run_layers_x(c->tcw, c->b, c->dims_in, c->dims_out, fused_split ? nullptr : c->hA, &c->actA, &c->actB,
                            nb, out, ldo,
                            want_depth ? -1.f : 0.f, prec, c->sm_count, st, &c->launches, c->mapc,
-                           out == c->flux ? c->actA.rows : 0);
+                           out == c->flux ? c->actA.rows : 0, c->use_stack ? &c->stackc : nullptr);
     *is_depth = want_depth ? 1 : 0;
     if (rc) return fail(rc, "tensor-core MLP path failed (precision " + std::to_string(prec) + ")");
   }
@@ -877,6 +879,7 @@ int payne_ctx_create(const PayneSpecNet* spec, const PaynePhotNet* phot, const P
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(PAYNE_E_UNSUPPORTED, "built for sm_100a (B200) only");
   PayneCtx* c = new PayneCtx();
+  { const char* e = getenv("PAYNE_GEMM_STACK"); c->use_stack = !(e && e[0] == '0'); }
   c->device = device; c->sm_count = prop.multiProcessorCount; c->lay = *layout;
   c->has_spec = layout->spec_bool != 0; c->has_phot = layout->phot_bool != 0;
   int rc = PAYNE_OK;
@@ -1087,6 +1090,7 @@ int64_t payne_ctx_query(PayneCtx* c, const char* key) {
   if (k == "gauss_stencil") return PAYNE_WITH_STENCIL && c->tail.gauss_stencil && c->fast.win_floats >= payne::kStSideFloats;
   if (k == "rot_window_floats") return c->fast.win_floats;
   if (k == "tail_cluster") return c->use_fast && c->allow_fast && c->use_cluster && c->allow_cluster;
+  if (k == "gemm_stack") return c->use_stack;
   if (k == "tail_clusters") return c->cluster_n;
   if (k == "tail_cluster_ctas_per_sm") return c->cluster_occ;
   if (k == "precision") return c->lay.precision;
@@ -1125,6 +1129,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   if (k == "timing") { c->timing = value != 0; return PAYNE_OK; }
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
   if (k == "tail_cluster") { c->allow_cluster = value != 0; return PAYNE_OK; }
+  if (k == "gemm_stack") { c->use_stack = value != 0; return PAYNE_OK; }
   if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)
