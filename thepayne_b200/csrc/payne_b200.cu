@@ -151,6 +151,8 @@ struct PayneCtx {
   int use_fast = 0;        // analytic-regrid tail selected (log-uniform emulator grid)
   int allow_fast = 1;
   // cluster-distributed fast tail (tail_cluster.cuh) for transforms above 16384 samples
+  int grid_cap = 0;        // > 0: at most this many CTAs (clusters) in the persistent tail grids (tests: forces the
+                           // dynamic point scheduling to hand several points to every CTA of a small batch)
   int use_cluster = 0, allow_cluster = 1;
   size_t cluster_smem = 0;
   int cluster_win_floats = 0, cluster_n = 0, cluster_occ = 0;
@@ -790,6 +792,7 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         CU_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
         c->fast.work_start = (c->use_cluster && c->allow_cluster) ? (int)std::min<long long>(c->cluster_n, nb)
                                                                   : std::min(c->tail_grid_fast, nb);
+        if (c->grid_cap > 0) c->fast.work_start = std::min(c->fast.work_start, c->grid_cap);
         if (payne::launch_tail_setup(nb, c->side, T, c->fast)) return fail(PAYNE_E_CUDA, "tail_setup launch");
         CU_TRY(cudaEventRecord(c->ev_join, c->side));
         c->launches++;
@@ -833,10 +836,10 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
       } else if (fast_tail && is_depth && c->use_cluster && c->allow_cluster) {
         payne::FastGrid FC = c->fast;
         FC.win_floats = c->cluster_win_floats;
-        if (payne::launch_tail_cluster(T.log2N1, (int)std::min<long long>(c->cluster_n, nb), c->cluster_smem, st, T, FC))
+        if (payne::launch_tail_cluster(T.log2N1, c->fast.work_start, c->cluster_smem, st, T, FC))
           return fail(PAYNE_E_CUDA, "tail launch");
       } else if (fast_tail && is_depth) {
-        const int grid = std::min(c->tail_grid_fast, nb);
+        const int grid = c->fast.work_start;
         const bool poly = T.n_poly != 0 || T.model_out != nullptr;
         if (payne::launch_tail_fast(T.log2N1, poly, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
       } else {
@@ -1130,6 +1133,7 @@ int payne_ctx_set(PayneCtx* c, const char* key, int64_t value) {
   if (k == "fast_tail") { c->allow_fast = value != 0; return PAYNE_OK; }
   if (k == "tail_cluster") { c->allow_cluster = value != 0; return PAYNE_OK; }
   if (k == "gemm_stack") { c->use_stack = value != 0; return PAYNE_OK; }
+  if (k == "tail_grid_cap") { c->grid_cap = (int)std::max<int64_t>(0, value); return PAYNE_OK; }
   if (k == "debug_skip") { c->tail.debug_skip = (int)value; return PAYNE_OK; }
   // Inst_R column holds the sigma-resolution getspec takes (predictspec.py:255-263) instead of the FWHM
   // resolution the likelihood samples (genmod.py:82-85)

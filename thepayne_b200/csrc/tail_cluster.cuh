@@ -372,6 +372,10 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
   // point i+1's successor while a slower CTA still reads point i's.
   __shared__ int c_next[2];
   int pn, it = 0;
+  // no CTA touches a peer's shared memory before every CTA of the cluster has started (compute-sanitizer flags the
+  // first remote stores otherwise); behind the loop nothing remote is pending: the last access to a peer lies before
+  // the last point's final cluster barrier
+  cl::cluster_sync();
   for (int p = (int)cl::cluster_id(); p < P.B; p = pn, it ^= 1) {
     float* row = P.flux + (long long)p * P.ldf;
     if (rank == 0 && tid == 0) {

@@ -16,3 +16,17 @@ for name, fast in [('mini_spec', 1), ('mini_spec', 0), ('mini_joint', 1), ('mini
     torch.cuda.synchronize()
     print(name, 'fast' if fast else 'general', 'max|dlnL|', float(np.nanmax(np.abs(l2.cpu().numpy() - g['lnl'][:len(th)]))))
     eng.close()
+# round 2: cluster tail (65536- and 32768-sample transforms over four CTAs, distributed shared memory), dynamic point
+# scheduling with a capped grid (every CTA claims several points), hidden-layer stack as one cluster launch
+for name, nrow in [('c4m', 3), ('mid', 5), ('c2', 7)]:
+    cfg, g = load_case(name)
+    eng = engine_from_config(cfg, precision='parity')
+    eng.set('tail_cluster', 1)
+    eng.set('tail_grid_cap', 2)
+    th = torch.from_numpy(g['theta'][:nrow]).cuda()
+    f, m, l = eng.model_batch(th)
+    l2 = eng.lnlike_batch(th)
+    torch.cuda.synchronize()
+    print(name, 'cluster' if eng.query('tail_cluster') else 'single-CTA', 'capped grid', 'max|dlnL|',
+          float(np.nanmax(np.abs(l2.cpu().numpy() - g['lnl'][:len(th)]))))
+    eng.close()
