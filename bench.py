@@ -225,8 +225,8 @@ def other_configs(precision):
     for key, builder, B, steps, what in [
             ('c3_joint', synth.config_c3, 16384, 5, 'C3: C2 + 7-band photometry (SED nets H=128), 16384 points'),
             ('c4_monolithic', synth.config_c4, 4096, 3,
-             'C4 (i): LinNet 5-512-512-512-51784, 65536-point transforms, n_obs 25000, order-4 continuum, Vrot<=100; '
-             '4096-point slabs of the 64k-point batch')]:
+             'C4 (i): LinNet 5-512-512-512-51784, 65536-sample transforms (one per cluster of four CTAs), n_obs 25000, '
+             'order-4 continuum, Vrot<=100; 4096-point slabs of the 64k-point batch')]:
         try:
             cfg = builder(gpu_model_fn)
             eng = engine_from_config(cfg, precision=precision)
@@ -244,6 +244,8 @@ def other_configs(precision):
             ms = e0.elapsed_time(e1) / steps
             out[key] = {'workload': what, 'points': B, 'ms_per_step': ms, 'value': B / (ms * 1e-3), 'unit': UNIT,
                         'finite_lnl': int(torch.isfinite(o).sum().item())}
+            if key == 'c4_monolithic':
+                out[key]['tail_cluster'] = int(eng.query('tail_cluster'))
             eng.close()
             del th, o
             torch.cuda.empty_cache()

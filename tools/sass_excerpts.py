@@ -9,12 +9,14 @@ def funcs(txt):
         if m: cur = m.group(1); out[cur] = []; continue
         if cur and re.match(r'\s+/\*[0-9a-f]{4,6}\*/', l): out[cur].append(l.rstrip())
     return out
-SPECIAL = ('UTC', 'UTMA', 'LDTM', 'FADD2', 'FFMA2', 'FMUL2', 'CCTL', 'SYNCS')
+SPECIAL = ('UTC', 'UTMA', 'LDTM', 'FADD2', 'FFMA2', 'FMUL2', 'CCTL', 'SYNCS', 'UCGABAR', 'MAPA', 'CGAERRBAR')
 rep = []
 B = 'thepayne_b200/csrc/_build/'
 for obj, pat, marks in [(B + 'gemm_tu.o', 'tc_gemm_kernelILi128ELi2ELi0ELi0E', ['UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM']),
                         (B + 'gemm_tu.o', 'tc_gemm_kernelILi64ELi2ELi1ELi0E', ['UTCHMMA', 'LDTM']),
-                        (B + 'tail_fast_tu.o', 'tail_fast_kernelILi14E', ['FADD2', 'LDS.128', 'CCTL'])]:
+                        (B + 'gemm_tu.o', 'tc_hidden_stack_kernel', ['UTCHMMA', 'UCGABAR_ARV', 'UTMALDG']),
+                        (B + 'tail_fast_tu.o', 'tail_fast_kernelILi14ELb0E', ['FADD2', 'LDS.128', 'CCTL', 'CALL']),
+                        (B + 'tail_cluster_tu.o', 'tail_cluster_kernelILi16E', ['UCGABAR_ARV', 'MAPA', 'ST.E.64', 'LD.E.64'])]:
     f = funcs(sass(obj))
     name = [k for k in f if pat in k][0]
     ins = f[name]
@@ -33,5 +35,6 @@ for obj, pat, marks in [(B + 'gemm_tu.o', 'tc_gemm_kernelILi128ELi2ELi0ELi0E', [
 open('profiles/r02_sass_excerpts.txt', 'w').write(
     '# cuobjdump -sass of the shipped objects (sm_100a): instruction census and excerpts around the Blackwell-specific\n'
     '# instructions -- UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor load / store, LDTM = tcgen05.ld (TMEM), UTCBAR =\n'
-    '# tcgen05.commit, SYNCS = mbarrier, FADD2 = packed fp32x2 add, CCTL.E.RML2 = discard.global.L2.\n\n' + '\n'.join(rep))
+    '# tcgen05.commit, SYNCS = mbarrier, FADD2 = packed fp32x2 add, CCTL.E.RML2 = discard.global.L2, UCGABAR_ARV / UCGABAR_WAIT =\n'
+    '# barrier.cluster.arrive / wait, MAPA = mapa.shared::cluster, ST.E.64 / LD.E.64 in the cluster tail = st / ld.shared::cluster (DSMEM).\n\n' + '\n'.join(rep))
 print('wrote profiles/r02_sass_excerpts.txt')
