@@ -192,8 +192,7 @@ int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
  * switches phases of the fused tail off, results are then meaningless; see csrc/tail.cuh).
  * Environment, read once: PAYNE_TAIL_CLUSTER=0 (never use the cluster tail) / 1 (also for 32768-sample transforms), PAYNE_ROT_WINDOW=0 (no shared-memory slice of the rotation-kernel table),
  * PAYNE_GEMM_PDL=0 (no programmatic dependent launch along the layer chain), PAYNE_GEMM_STACK=0 (see "gemm_stack"),
- * PAYNE_GEMM_MULTICAST=1 / PAYNE_GEMM_2SM=1|2 (experimental GEMM variants: weight multicast, cta_group::2
- * pair tiles 256x128 / 256x256; bit-exact, slower or equal). */
+ * PAYNE_GEMM_MULTICAST=1 (experimental GEMM variant: 2-CTA weight multicast; bit-exact, same speed). */
 int payne_ctx_set(PayneCtx* ctx, const char* key, int64_t value);
 
 /* Kernel unit-test hook: C[M,N] = A[M,K] . W[N,K]^T + bias[N] through the tensor-core GEMM of

@@ -106,43 +106,6 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 template <int NTHREADS>
 __device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-// ---- cta_group::2 (two SMs on one tile) ----
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even CTA
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arrive on the even CTA's barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void mma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -235,9 +198,6 @@ __device__ __forceinline__ void x3_split_act(float h, __nv_bfloat16& p1, __nv_bf
 #ifndef PAYNE_LIN6_BN
 #define PAYNE_LIN6_BN 128
 #endif
-#ifndef PAYNE_GEMM_2SM_DEFAULT
-#define PAYNE_GEMM_2SM_DEFAULT 0
-#endif
 constexpr int kTcThreads = 256;
 // Hidden layers (sigmoid + operand slicing epilogue, ~40 dependent instructions per element) get four
 // groups of four epilogue warps: with one warp per scheduler the epilogue ran at IPC 0.16 and took more
@@ -282,35 +242,6 @@ __device__ __forceinline__ void epi_store_block(const CUtensorMap* cmap, float* 
   ptx::fence_async_smem();
   __syncwarp();
   if (lane == 0) ptx::tma_store_2d(cmap, stage, gcol0, grow0);
-}
-
-// Staging-free variant for the pair-tile kernel (its three-stage ring leaves no shared memory for the
-// TMA-store blocks): thread = row, whose 32 columns are 128 contiguous bytes, written as eight 16-byte
-// stores -- every store fills half a sector of its own line, the eight together the whole line.
-__device__ __forceinline__ void epi_store_direct(float* out, long long ldc, int M, int N, const float* sb,
-                                                 const float* ss, const uint32_t (&v)[32], const uint32_t (&c)[32],
-                                                 int colbase, int gcol0, int grow) {
-  if (grow >= M) return;
-  const float4* b4 = reinterpret_cast<const float4*>(sb + colbase);
-  const float4* s4 = reinterpret_cast<const float4*>(ss + colbase);
-  float* dst = out + (long long)grow * ldc + gcol0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4 bb = b4[k], sc = s4[k];
-    float4 o;
-    o.x = fmaf(__uint_as_float(v[4 * k + 0]) + __uint_as_float(c[4 * k + 0]), sc.x, bb.x);
-    o.y = fmaf(__uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1]), sc.y, bb.y);
-    o.z = fmaf(__uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]), sc.z, bb.z);
-    o.w = fmaf(__uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]), sc.w, bb.w);
-    const int gc = gcol0 + 4 * k;
-    if (gc + 4 <= N) {
-      *reinterpret_cast<float4*>(dst + 4 * k) = o;
-    } else {
-      if (gc + 0 < N) dst[4 * k + 0] = o.x;
-      if (gc + 1 < N) dst[4 * k + 1] = o.y;
-      if (gc + 2 < N) dst[4 * k + 2] = o.z;
-    }
-  }
 }
 
 template <int BN, int MODE>
@@ -639,179 +570,6 @@ tc_gemm_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmA
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// ------------------------------------------------------------------------------------------------
-// lin6 on CTA PAIRS (cta_group::2): a 2-CTA cluster owns a 256 x BN output tile; CTA r holds rows
-// [128 r, 128 r + 128) of the activations and weight rows [BN/2 r, +BN/2) of the tile, the leader
-// (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) and each SM accumulates its 128 rows in its own
-// TMEM.  Inbound operand traffic per SM drops relative to the 128 x 128 single-CTA tiles.  X3 only.
-// Measured on B200: bit-exact, but 50 % tensor-pipe utilisation against 74 % for the single-CTA kernel
-// (profiles/r01_gemm_l6_pairtile.txt) -- opt-in until that is understood.
-__host__ __device__ constexpr uint32_t umma_idesc_m256(int N, uint32_t fmt) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
-// BN = 256: one 512-column accumulator pair, 2-deep ring (epilogue exposed).  BN = 128: the pair tile is
-// 256 x 128, each CTA stages its 128 activation rows and 64 of the weight rows (72 KB per k-block instead
-// of 96 KB for the single-CTA 128 x 128 tile), which buys a 3-deep ring, and two accumulator pairs fit
-// the 512 TMEM columns so the epilogue overlaps the next tile's MMAs.
-template <int BN>
-struct Tc2Cfg {
-  static constexpr int BNH = BN / 2, NP = 3;
-  static constexpr int NS = BN == 128 ? 3 : 2;
-  static constexpr int NACC = BN == 128 ? 2 : 1;
-  static constexpr int kABytes = kBM * kRowBytes, kBBytes = BNH * kRowBytes;
-  static constexpr int kStageBytes = NP * (kABytes + kBBytes);          // per CTA
-  static constexpr int kStagingBytes = BN == 128 ? 0 : 4 * 4096;       // TMA-store staging (BN = 128 stores directly)
-  static constexpr int kSmem = NS * kStageBytes + kStagingBytes + 1024 + 256 + 2 * BN * 4;
-  static_assert(kSmem <= 232448, "shared memory budget");
-};
-
-template <int EPI, int BN>
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm2_kernel(const __grid_constant__ TcMaps T, const __grid_constant__ TcGemmArgs G) {
-  using C2 = Tc2Cfg<BN>;
-  constexpr int BNH = C2::BNH, NP = C2::NP, NS = C2::NS, NACC = C2::NACC;
-  constexpr int kABytes = C2::kABytes, kBBytes = C2::kBBytes, kStageBytes = C2::kStageBytes;
-  constexpr int kBK = 64;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  unsigned char* stages = base;
-  float* patch = (float*)(base + NS * kStageBytes);
-  uint64_t* bars = (uint64_t*)((unsigned char*)patch + C2::kStagingBytes);
-  uint64_t* full = bars;             // [NS]  used in the leader: 2 arrivals + bytes of both CTAs
-  uint64_t* empty = bars + NS;       // [NS]  per CTA: multicast commit of the leader
-  uint64_t* tfull = bars + 2 * NS;   // [NACC] per CTA: multicast commit of the leader
-  uint64_t* tempty = tfull + NACC;   // [NACC] leader: 8 epilogue warps (both CTAs)
-  uint32_t* tmem_ptr = (uint32_t*)(tempty + NACC);
-  float* sbias = (float*)(bars + 32);
-  float* sscale = sbias + BN;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = ptx::cluster_ctarank();
-  const bool leader = crank == 0;
-  const int num_mp = (G.M + 255) / 256, num_n = (G.N + BN - 1) / BN;
-  const int num_tiles = num_mp * num_n;
-  const int num_kb = (G.K + kBK - 1) / kBK;
-  const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);
-
-  if (warp == 0 && lane == 0) {
-    for (int p = 0; p < NP; ++p) { ptx::prefetch_tmap(&T.a[p]); ptx::prefetch_tmap(&T.b[p]); }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NS; ++s) { ptx::mbar_init(&full[s], 2); ptx::mbar_init(&empty[s], 1); }
-    for (int a = 0; a < NACC; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 8); }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr, 512);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync_all();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs); bytes and arrivals go to the leader's barrier
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        const int m0 = (tile / num_n) * 256 + (int)crank * 128, n0 = (tile % num_n) * BN + (int)crank * BNH;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait_cluster(&empty[s], ph ^ 1);
-          unsigned char* st = stages + s * kStageBytes;
-          if (leader) ptx::mbar_expect_tx(&full[s], 2 * kStageBytes);
-          const int k0 = kb * kBK;
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            ptx::tma_load_2d_2sm(&T.a[p], &full[s], st + p * kABytes, k0, m0);
-            ptx::tma_load_2d_2sm(&T.b[p], &full[s], st + NP * kABytes + p * kBBytes, k0, n0);
-          }
-          if (!leader) ptx::mbar_arrive_leader(&full[s]);
-          if (++s == NS) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader only)
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_m256(BN, 1u);
-      int s = 0; uint32_t ph = 0;
-      int acc = 0; uint32_t aph = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        ptx::mbar_wait_cluster(&tempty[acc], aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN), d_corr = d_main + BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait_cluster(&full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t st = ptx::smem_u32(stages + s * kStageBytes);
-          uint64_t da[3], db[3];
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            da[p] = umma_desc_k_sw128(st + p * kABytes);
-            db[p] = umma_desc_k_sw128(st + NP * kABytes + p * kBBytes);
-          }
-#pragma unroll
-          for (int ks = 0; ks < kBK / 16; ++ks) {
-            const uint64_t ko = (uint64_t)((ks * 32) >> 4);
-            const uint32_t first = (kb | ks) != 0;
-            ptx::mma_bf16_2sm(d_main, da[0] + ko, db[0] + ko, idesc, first);
-            ptx::mma_bf16_2sm(d_corr, da[0] + ko, db[2] + ko, idesc, first);
-            ptx::mma_bf16_2sm(d_corr, da[1] + ko, db[1] + ko, idesc, 1);
-            ptx::mma_bf16_2sm(d_corr, da[2] + ko, db[0] + ko, idesc, 1);
-            ptx::mma_bf16_2sm(d_corr, da[0] + ko, db[1] + ko, idesc, 1);
-            ptx::mma_bf16_2sm(d_corr, da[1] + ko, db[0] + ko, idesc, 1);
-          }
-          ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)3);
-          if (kb == num_kb - 1) ptx::mma_commit_2sm_mc(&tfull[acc], (uint16_t)3);
-          if (++s == NS) { s = 0; ph ^= 1; }
-        }
-        if (++acc == NACC) { acc = 0; aph ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 rows)
-    const int q = warp & 3;
-    float* pt = patch + q * (C2::kStagingBytes / 16);
-    int acc = 0; uint32_t aph = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tstep) {
-      const int m0 = (tile / num_n) * 256 + (int)crank * 128, n0 = (tile % num_n) * BN;
-      ptx::epi_bar_sync();
-      for (int cix = threadIdx.x - 128; cix < BN; cix += 128) {
-        const int gc = n0 + cix;
-        sbias[cix] = (gc < G.N ? __ldg(G.bias + gc) : 0.f) + G.bias_shift;
-        sscale[cix] = gc < G.N ? __ldg(G.wscale + gc) : 1.f;
-      }
-      ptx::epi_bar_sync();
-      ptx::mbar_wait_cluster(&tfull[acc], aph);
-      ptx::tc_fence_after();
-      const int row_base = m0 + q * 32;
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int col0 = n0 + ch * 32;
-        if (col0 >= G.N) break;
-        uint32_t v[32], c[32];
-        ptx::tmem_ld32_nowait(t_main + (uint32_t)(ch * 32), v);
-        ptx::tmem_ld32_nowait(t_main + (uint32_t)(BN + ch * 32), c);
-        ptx::tmem_ld_wait();
-        if constexpr (BN == 128)
-          epi_store_direct((float*)G.out0, G.ldc, G.M, G.N, sbias, sscale, v, c, ch * 32, col0, row_base + lane);
-        else
-          epi_store_block<true>(&T.c, pt, sbias, sscale, v, c, ch * 32, col0, row_base, lane);
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_leader(&tempty[acc]);
-      if (++acc == NACC) { acc = 0; aph ^= 1; }
-    }
-    if (lane == 0) ptx::tma_store_wait_all();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync_all();
-  if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
-}
-
 // fp32 -> operand planes of the next GEMM
 static __global__ void tf32_split_kernel(const float* __restrict__ src, long long lds, float* __restrict__ hi,
                                   float* __restrict__ lo, long long ldd, long long rows, int cols) {
@@ -1128,47 +886,6 @@ inline int tc_launch_impl(const TcActs& A, int K, const TcWeights& W, const floa
   return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
 }
 
-// PAYNE_GEMM_2SM selects the cta_group::2 pair-tile kernel for lin6: 1 = 256 x 128 pair tiles (3-deep ring,
-// double-buffered accumulators), 2 = 256 x 256 pair tiles (single accumulator pair, epilogue exposed),
-// 0 = single-CTA 128 x 128 tiles.
-inline int tc_2sm_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PAYNE_GEMM_2SM"); v = e ? atoi(e) : PAYNE_GEMM_2SM_DEFAULT; if (v < 0 || v > 2) v = 0; }
-  return v;
-}
-
-template <int BN>
-inline int tc_launch_2sm(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, long long ldc,
-                         float bias_shift, int M, int sm_count, cudaStream_t st, long long map_rows) {
-  using C2 = Tc2Cfg<BN>;
-  const long long mrows = map_rows >= M ? map_rows : M;
-  TcMaps T;
-  for (int p = 0; p < 3; ++p) {
-    if (make_tmap(&T.a[p], A.plane[p], mrows, K, A.ld, kBM, 2)) return PAYNE_E_CUDA;
-    if (make_tmap(&T.b[p], W.xplane[p], W.N, K, W.Kp, C2::BNH, 2)) return PAYNE_E_CUDA;
-  }
-  if (int rc = make_tmap_out(&T.c, out0, mrows, W.N, ldc)) return rc;
-  static unsigned long long attr_set = 0;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return PAYNE_E_CUDA;
-  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
-    if (cudaFuncSetAttribute(tc_gemm2_kernel<0, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem) != cudaSuccess)
-      return PAYNE_E_CUDA;
-    if (dev < 64) attr_set |= 1ull << dev;
-  }
-  TcGemmArgs G{bias, W.scale, nullptr, out0, nullptr, nullptr, ldc, bias_shift, M, W.N, K, 1, W.N, 0, 0, 0};
-  const int pair_tiles = ((M + 255) / 256) * ((W.N + BN - 1) / BN);
-  const int grid = 2 * pair_tiles < (sm_count & ~1) ? 2 * pair_tiles : (sm_count & ~1);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = C2::kSmem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<0, BN>, T, G) != cudaSuccess) return PAYNE_E_CUDA;
-  return cudaGetLastError() == cudaSuccess ? PAYNE_OK : PAYNE_E_CUDA;
-}
-
 template <int BN, int MODE, int EPI>
 inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bias, void* out0, void* out1,
                      void* out2, long long ldc, float bias_shift, int M, int sm_count, cudaStream_t st,
@@ -1180,10 +897,6 @@ inline int tc_launch(const TcActs& A, int K, const TcWeights& W, const float* bi
   if (grp && grp->groups > 1)
     return tc_launch_impl<BN, MODE, EPI, 0>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
                                             map_rows, grp, out_cols);
-  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 1)
-    return tc_launch_2sm<128>(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st, map_rows);
-  if (MODE == kModeX3 && EPI == 0 && M > kBM && tc_2sm_mode() == 2)
-    return tc_launch_2sm<256>(A, K, W, bias, out0, ldc, bias_shift, M, sm_count, st, map_rows);
   // multicast pays when many row tiles share each weight tile (the wide last layer)
   if (EPI == 0 && BN >= 128 && M > kBM && tc_multicast_enabled())
     return tc_launch_impl<BN, MODE, EPI, 1>(A, K, W, bias, out0, out1, out2, ldc, bias_shift, M, sm_count, st, cache,
