@@ -371,7 +371,7 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
   // CTA's c_next[parity]; the point's last cluster barrier publishes it.  Two slots: CTA 0 may already be posting
   // point i+1's successor while a slower CTA still reads point i's.
   __shared__ int c_next[2];
-  int pn, it = 0;
+  int pn, it = 0, win_have = 0;
   // no CTA touches a peer's shared memory before every CTA of the cluster has started (compute-sanitizer flags the
   // first remote stores otherwise); behind the loop nothing remote is pending: the last access to a peer lies before
   // the last point's final cluster barrier
@@ -405,7 +405,8 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
       const double xt_max = S.vsini_scale * (double)(N1 >> 1);
       float4* win4 = reinterpret_cast<float4*>(win);
       const int nwin = (int)fmin(fmin(xt_max + 2.0, (double)(F.win_floats >> 2)), (double)P.ntab);
-      for (int i = tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);     // published by the first cluster barrier
+      for (int i = win_have + tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);     // published by the first cluster barrier
+      win_have = max(win_have, nwin);                     // what an earlier point staged stays valid
       const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab, RotHT<2>::fix40(S.vsini_scale)};
       cl::convolve_regrid<LOG2MQ>(z, zb, rank, tw, F.twc, H, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native, S.clean != 0, 0);
       // back onto the emulator grid: this CTA makes the pixels whose left sample floor(i b_num / b_den) it holds

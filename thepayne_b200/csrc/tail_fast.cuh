@@ -361,6 +361,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
   // static shared memory would come out of every point's rotation-table window)
   int& s_next = *reinterpret_cast<int*>(&red[0]);
   int pn;
+  int win_have = 0;                                       // table intervals already in the window
   for (int p = blockIdx.x; p < P.B; p = pn) {
     float* row = P.flux + (long long)p * P.ldf;
     // the next point is claimed now (its latency hides under this point) and read after the barrier below; thread 0
@@ -389,7 +390,10 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       // from the global table)
       float4* win4 = reinterpret_cast<float4*>(win);
       const int nwin = (int)fmin(fmin(xt_max + 2.0, (double)(F.win_floats >> 2)), (double)P.ntab);
-      for (int i = tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);
+      // (the window holds the first intervals of the one table: what an earlier point of this CTA staged stays valid)
+      if (PAYNE_WITH_STENCIL) win_have = 0;               // (the stencil stage reuses the window's space)
+      for (int i = win_have + tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);
+      win_have = max(win_have, nwin);
       // (one filter instantiation with a per-lookup choice: a second, window-only copy of the filter stage
       // measured 1.7 % slower -- code size and register allocation at the 80-register cap)
       const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab, RotHT<2>::fix40(S.vsini_scale)};
