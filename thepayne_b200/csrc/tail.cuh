@@ -144,7 +144,7 @@ struct RotHT {
     return scale < 256.0 ? (unsigned long long)__double2ll_rn(scale * 1099511627776.0) : ~0ull;
   }
   __device__ __forceinline__ float operator()(int k) const {
-    if (s40 == ~0ull) return direct(scale * (double)k * h) * invM;     // absurdly broad kernel: closed form
+    if (WINDOW != 1 && s40 == ~0ull) return direct(scale * (double)k * h) * invM;     // absurdly broad kernel: closed form
     const unsigned long long pos = (unsigned long long)(unsigned)k * s40;
     const int i = (int)(pos >> 40);
     if (WINDOW != 1 && i >= ntab) return direct(scale * (double)k * h) * invM;

@@ -28,6 +28,12 @@
 #ifndef PAYNE_WITH_STENCIL
 #define PAYNE_WITH_STENCIL 0
 #endif
+// A second, window-only instantiation of the rotation filter for points whose whole table range is staged (no per-lookup
+// choice, no table-end test) measured 1 % SLOWER at C2 both in round 2's first build (1.7 %) and with the shared passes
+// (0.6825 -> 0.689 ms, A/B on one box): off.
+#ifndef PAYNE_ROT_WINONLY
+#define PAYNE_ROT_WINONLY 0
+#endif
 
 namespace payne {
 
@@ -394,15 +400,28 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       if (PAYNE_WITH_STENCIL) win_have = 0;               // (the stencil stage reuses the window's space)
       for (int i = win_have + tid; i < nwin; i += kNT) win4[i] = __ldg(P.sbtab + i);
       win_have = max(win_have, nwin);
-      // (one filter instantiation with a per-lookup choice: a second, window-only copy of the filter stage
-      // measured 1.7 % slower -- code size and register allocation at the 80-register cap)
+      // (one filter instantiation with a per-lookup choice: see PAYNE_ROT_WINONLY)
       const RotHT<2> H{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, 1.0f / (float)(N1 >> 1), P.ntab, RotHT<2>::fix40(S.vsini_scale)};
       // pixels stage 2 will read: its mask [i0, i1] (one more on each side keeps the edge patch exact)
       const int blo = S.use_inst ? max(S.i0 - 1, 0) : 0, bhi = S.use_inst ? min(S.i1 + 1, n - 1) : n - 1;
       if constexpr (!kSplit) {
         // regrid fused into the first FFT pass (measured against the separate regrid: tail -5 %)
-        if (!(P.debug_skip & 1))
+        if (!(P.debug_skip & 1)) {
+#if PAYNE_ROT_WINONLY
+          // a point whose whole table range sits in the window (vsini <= ~5 km/s at C2) takes the filter
+          // instantiation without the per-lookup choice and the table-end test; only the filter stage is duplicated
+          ct_convolve_regrid_fwd<LOG2N1 - 1>(z, tw, F.twc, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native, S.clean != 0);
+          if (xt_max + 2.0 <= (double)nwin && H.s40 != ~0ull) {
+            const RotHT<1> H1{P.sbtab, win4, nwin, S.vsini_scale, P.sb_h, H.invM, P.ntab, H.s40};
+            ct_filter_pairs<LOG2N1 - 1>(z, tw, H1, tid);
+          } else {
+            ct_filter_pairs<LOG2N1 - 1>(z, tw, H, tid);
+          }
+          ct_convolve_inv<LOG2N1 - 1>(z, tw, F.twc, tid);
+#else
           ct_convolve_regrid<LOG2N1 - 1>(z, tw, F.twc, H, tid, row, F.f_num, F.f_den, F.f_invden, F.c_native, S.clean != 0);
+#endif
+        }
         if (!(P.debug_skip & 8)) regrid_back(row, zs, F, tid, n, N1, blo, bhi);
       } else {
         stage_regrid(S, row, zp, tid, N1, F.f_num, F.f_den, 0, F.f_invden, F.c_native, F.f_incj, F.f_incr);
