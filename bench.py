@@ -388,10 +388,21 @@ def run_ours(args):
     else:
         theta_pin = torch.from_numpy(theta_h).pin_memory()
         lnl_pin = torch.empty(world * B, dtype=torch.float64).pin_memory()
+        # every step needs ITS gathered vector (nothing to pipeline behind): the library's own all-gather over peer
+        # memory (payne_gather_*: one push kernel + flags, ~13 us at 8 GPUs) instead of a blocking ncclAllGather
+        try:
+            peer = pdist.PeerGather(eng, B)
+            e2e_gather = 'peer memory (payne_lnlike_batch_gather + payne_gather_flush)'
+        except Exception as exc:                     # raised on every rank alike
+            peer, e2e_gather = None, 'ncclAllGather (peer memory unavailable: %s)' % str(exc)[:80]
 
         def e2e_step():
             th = theta_pin.cuda(non_blocking=True)
-            g = pdist.gather_equal(eng.lnlike_batch(th))
+            if peer is not None:
+                peer.submit(th)
+                g = peer.flush()
+            else:
+                g = pdist.gather_equal(eng.lnlike_batch(th))
             lnl_pin.copy_(g, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return lnl_pin.numpy()
@@ -491,7 +502,7 @@ def run_ours(args):
         'e2e': {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(theta_h.nbytes),
                 'd2h_bytes_per_step': int(lnl_h.nbytes),
                 'path': 'payne_lnlike_batch_host (C ABI, host buffers)' if world == 1 else
-                        'pinned theta -> H2D -> payne_lnlike_batch -> ncclAllGather(lnL) -> D2H'},
+                        'pinned theta -> H2D -> likelihood -> all-gather of lnL over %s -> D2H' % e2e_gather},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'tail_fast_kernel<%d> (+tail_setup_kernel)' % int(np.log2(eng.query('nfft1'))), 'bound': 'hbm', 'achieved': tail_gbs, 'peak': hbm, 'unit': 'GB/s',
                      'frac': tail_gbs / hbm, 'traffic': traffic, 'algorithmic_bytes': tail_bytes, 'peak_source': which, 'ms_per_launch': tail_ms,

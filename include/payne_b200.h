@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define PAYNE_ABI_VERSION 4
+#define PAYNE_ABI_VERSION 5
 
 enum {
   PAYNE_OK = 0,
@@ -180,10 +180,30 @@ int payne_ctx_set_lsf(PayneCtx* ctx, const double* lsf_host, int64_t n);
 int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, int64_t ldy,
                    void* stream);
 
+/* Multi-GPU: all-gather of lnL over peer memory (one process per GPU on one node; replaces the ncclAllGather behind
+ * every step of the sharded likelihood, thepayne_b200/dist.py).  Every rank holds three rotating buffers of
+ * world * slots doubles.  payne_gather_create allocates them and writes PAYNE_GATHER_HANDLE_BYTES of CUDA IPC handles to
+ * handles_out; the ranks exchange those bytes (any transport: the Python side uses torch.distributed's all_gather_object)
+ * and pass the concatenation, in rank order, to payne_gather_connect, which maps the peers' buffers (NVLink P2P).
+ * payne_lnlike_batch_gather = payne_lnlike_batch of this rank's B = slots points, its lnL written into this rank's slice
+ * and pushed into every rank's buffer by one kernel (plain stores through the peer mappings, then a flag per rank behind a
+ * system-scope fence); stream-ordered, no host synchronisation, every rank must call it the same number of times.
+ * *gathered_prev receives the device pointer of the complete gathered vector [world * slots] of the PREVIOUS call (NULL on
+ * the first): it is valid for work enqueued on `stream` after this call and must be consumed before the next call.
+ * payne_gather_flush enqueues the wait for the last step and returns its vector.  A peer that never arrives sets
+ * status bit 1 after ~10 s instead of hanging the device. */
+#define PAYNE_GATHER_HANDLE_BYTES 128
+int payne_gather_create(PayneCtx* ctx, int world, int rank, int64_t slots, void* handles_out);
+int payne_gather_connect(PayneCtx* ctx, const void* all_handles);
+int payne_lnlike_batch_gather(PayneCtx* ctx, const double* theta_dev, int64_t B, int64_t ld, void* stream,
+                              double** gathered_prev);
+int payne_gather_flush(PayneCtx* ctx, void* stream, double** gathered_last);
+
 /* Introspection for benches/tests: key is one of "n_ann","n_obs","nfft1","launches",
  * "grid_loguniform","fast_tail","max_batch","sm_count","tail_grid","precision","continuum","lsf","legacy_tc"
  * (a leaky-ReLU stack whose output layer runs on the tensor cores),"status"
- * (bit0: a point needed a larger transform than the shared-memory carve-out). Returns the value or -1. */
+ * (bit0: a point needed a larger transform than the shared-memory carve-out; bit1: a peer of the gather never arrived).
+ * Returns the value or -1. */
 int64_t payne_ctx_query(PayneCtx* ctx, const char* key);
 /* Runtime switches: "precision" (PAYNE_PREC_*), "max_batch" (workspace slab, points), "timing" (0/1,
  * see payne_ctx_last_ms), "fast_tail" (0 forces the general-grid tail), "gemm_stack" (0: one launch per hidden layer instead of

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PAYNE_LIB_PATH: development override (an instrumented build of the same sources)
 LIB_PATH = os.environ.get('PAYNE_LIB_PATH') or os.path.join(HERE, 'libpayne_b200.so')
 
-ABI_VERSION = 4          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
+ABI_VERSION = 5          # PAYNE_ABI_VERSION of include/payne_b200.h the ctypes structs below mirror
 NPAR = 13
 MAX_POLY = 16
 PAR_INDEX = {
@@ -24,7 +24,9 @@ PREC = {'parity': 0, 'x3': 0, 'tf32': 1, 'bf16': 2, 'simt': 3, 'fp32': 3, '3xtf3
 EXPORTS = ['payne_abi_version', 'payne_last_error', 'payne_ctx_create', 'payne_ctx_destroy',
            'payne_lnlike_batch', 'payne_lnlike_batch_host', 'payne_model_batch', 'payne_ann_eval',
            'payne_ctx_query', 'payne_ctx_set', 'payne_ctx_last_ms', 'payne_gemm_test',
-           'payne_ctx_attach_continuum', 'payne_ctx_set_lsf']
+           'payne_ctx_attach_continuum', 'payne_ctx_set_lsf',
+           'payne_gather_create', 'payne_gather_connect', 'payne_lnlike_batch_gather', 'payne_gather_flush']
+GATHER_HANDLE_BYTES = 128
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)
@@ -96,6 +98,14 @@ def load():
     lib.payne_ctx_attach_continuum.argtypes = [vp, C.POINTER(PayneSpecNet)]
     lib.payne_ctx_set_lsf.restype = C.c_int
     lib.payne_ctx_set_lsf.argtypes = [vp, vp, C.c_int64]
+    lib.payne_gather_create.restype = C.c_int
+    lib.payne_gather_create.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp]
+    lib.payne_gather_connect.restype = C.c_int
+    lib.payne_gather_connect.argtypes = [vp, vp]
+    lib.payne_lnlike_batch_gather.restype = C.c_int
+    lib.payne_lnlike_batch_gather.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.POINTER(vp)]
+    lib.payne_gather_flush.restype = C.c_int
+    lib.payne_gather_flush.argtypes = [vp, vp, C.POINTER(vp)]
     lib.payne_ctx_query.restype = C.c_int64
     lib.payne_ctx_query.argtypes = [vp, C.c_char_p]
     lib.payne_ctx_set.restype = C.c_int

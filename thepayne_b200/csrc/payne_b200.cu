@@ -175,6 +175,16 @@ struct PayneCtx {
   payne::TcActs actA, actB;
   double* chi2_sed = nullptr;
   int* status = nullptr;
+  // all-gather of lnL over peer memory (payne_gather_*): three rotating buffers [world * slots] on every rank, each
+  // rank's push kernel stores its slice into every rank's copy and then raises its flag there
+  int g_world = 0, g_rank = 0;
+  long long g_slots = 0, g_seq = 0;            // g_seq: steps submitted so far
+  double* g_buf = nullptr;                      // local [3][world * slots]
+  unsigned long long* g_flag = nullptr;         // local [world]: last step whose slice of rank r has landed here (+1)
+  double* g_peer_buf[16] = {nullptr};           // every rank's g_buf as mapped into this process (own = local)
+  unsigned long long* g_peer_flag[16] = {nullptr};
+  bool g_opened[16] = {false};
+  int* g_done = nullptr;                        // CTA counter of the push kernel
   // host staging
   long long stage_cap = 0, stage_ld = 0;
   double *theta_pin = nullptr, *lnl_pin = nullptr, *theta_stage = nullptr, *lnl_stage = nullptr;
@@ -912,6 +922,9 @@ void payne_ctx_destroy(PayneCtx* c) {
   c->fast.points = nullptr; drop(c->status);
   payne::tc_free_acts_x(&c->actA); payne::tc_free_acts_x(&c->actB);
   drop(c->theta_stage); drop(c->lnl_stage);
+  for (int r = 0; r < 16; ++r)
+    if (c->g_opened[r]) { cudaIpcCloseMemHandle(c->g_peer_buf[r]); cudaIpcCloseMemHandle(c->g_peer_flag[r]); }
+  drop(c->g_buf); drop(c->g_flag); drop(c->g_done);
   if (c->theta_pin) cudaFreeHost(c->theta_pin);
   if (c->lnl_pin) cudaFreeHost(c->lnl_pin);
   for (auto& evs : c->pending) for (auto e : evs) cudaEventDestroy(e);
@@ -975,6 +988,164 @@ int payne_lnlike_batch_host(PayneCtx* c, const double* theta_host, int64_t B, in
                            c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   std::memcpy(lnl_host, c->lnl_pin, (size_t)B * sizeof(double));
+  return PAYNE_OK;
+}
+
+}  // extern "C"
+
+// ---- all-gather of lnL over peer memory --------------------------------------------------------------------
+// One kernel per step instead of a collective library call: thread 0 first waits until every rank's slice of
+// the PREVIOUS step has landed here (flags; this also makes the buffer about to be overwritten on the peers free,
+// see payne_lnlike_batch_gather), then every thread copies its share of this rank's lnL slice into every rank's
+// buffer with plain stores through the NVLink peer mappings; the last CTA to finish raises this rank's flag on
+// every rank behind a system-scope fence.
+namespace {
+struct GatherPush {
+  const double* src;                 // this rank's slice [n] (inside its own buffer)
+  double* dst[16];                   // every rank's buffer for this step, already offset to this rank's slice
+  unsigned long long* flag[16];      // every rank's flag word of THIS rank
+  const unsigned long long* local_flags;   // this rank's flag array [world]
+  unsigned long long wait_for;       // flags must have reached this value (0: nothing to wait for)
+  unsigned long long raise_to;
+  int world, rank, n;
+  int* done;
+  int* status;
+};
+
+// One CTA: 32 KB per rank and step is latency, not bandwidth -- a single system-scope fence behind the stores, then the flags.
+__global__ void __launch_bounds__(1024) gather_push_kernel(const __grid_constant__ GatherPush G) {
+  if (G.wait_for && threadIdx.x < G.world) {
+    const volatile unsigned long long* f = G.local_flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < G.wait_for) {
+      if (clock64() - t0 > 20000000000LL) { atomicOr(G.status, 2); break; }     // ~10 s: a peer is gone
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int n2 = G.n >> 1;                                  // pairs: 16-byte stores (slices are 16-byte aligned when n is even)
+  const bool vec = (G.n & 1) == 0;
+  if (vec) {
+    const double2* s2 = reinterpret_cast<const double2*>(G.src);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double2 v = s2[i];
+      for (int r = 0; r < G.world; ++r)
+        if (r != G.rank) reinterpret_cast<double2*>(G.dst[r])[i] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < G.n; i += blockDim.x) {
+      const double v = G.src[i];
+      for (int r = 0; r < G.world; ++r)
+        if (r != G.rank) G.dst[r][i] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < G.world) {
+    __threadfence_system();                                  // (cumulative: orders every thread's stores before the flag)
+    *reinterpret_cast<volatile unsigned long long*>(G.flag[threadIdx.x]) = G.raise_to;
+  }
+}
+
+__global__ void gather_wait_kernel(const unsigned long long* flags, unsigned long long wait_for, int world, int* status) {
+  if ((int)threadIdx.x < world) {
+    const volatile unsigned long long* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < wait_for) {
+      if (clock64() - t0 > 20000000000LL) { atomicOr(status, 2); break; }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int payne_gather_create(PayneCtx* c, int world, int rank, int64_t slots, void* handles_out) {
+  if (!c || !handles_out) return fail(PAYNE_E_INVALID, "null argument");
+  if (world < 1 || world > 16 || rank < 0 || rank >= world || slots < 1) return fail(PAYNE_E_INVALID, "bad world / rank / slots");
+  if (c->g_buf) return fail(PAYNE_E_INVALID, "gather already created on this context");
+  DeviceGuard dg(c->device);
+  c->g_world = world; c->g_rank = rank; c->g_slots = slots; c->g_seq = 0;
+  const size_t nb = (size_t)3 * world * slots * sizeof(double);
+  CU_TRY(cudaMalloc((void**)&c->g_buf, nb));
+  CU_TRY(cudaMemset(c->g_buf, 0, nb));
+  CU_TRY(cudaMalloc((void**)&c->g_flag, 16 * sizeof(unsigned long long)));
+  CU_TRY(cudaMemset(c->g_flag, 0, 16 * sizeof(unsigned long long)));
+  CU_TRY(cudaMalloc((void**)&c->g_done, sizeof(int)));
+  CU_TRY(cudaMemset(c->g_done, 0, sizeof(int)));
+  CU_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h[2];
+  CU_TRY(cudaIpcGetMemHandle(&h[0], c->g_buf));
+  CU_TRY(cudaIpcGetMemHandle(&h[1], c->g_flag));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI (PAYNE_GATHER_HANDLE_BYTES)");
+  std::memcpy(handles_out, h, sizeof(h));
+  c->g_peer_buf[rank] = c->g_buf; c->g_peer_flag[rank] = c->g_flag;
+  return PAYNE_OK;
+}
+
+int payne_gather_connect(PayneCtx* c, const void* all_handles) {
+  if (!c || !all_handles) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->g_buf) return fail(PAYNE_E_INVALID, "payne_gather_create first");
+  DeviceGuard dg(c->device);
+  const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < c->g_world; ++r) {
+    if (r == c->g_rank) continue;
+    void *pb = nullptr, *pf = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, h[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pf, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(PAYNE_E_UNSUPPORTED, "peer memory of rank " + std::to_string(r) + " cannot be mapped (no P2P path?)");
+    }
+    c->g_peer_buf[r] = (double*)pb; c->g_peer_flag[r] = (unsigned long long*)pf; c->g_opened[r] = true;
+  }
+  return PAYNE_OK;
+}
+
+int payne_lnlike_batch_gather(PayneCtx* c, const double* theta_dev, int64_t B, int64_t ld, void* stream,
+                              double** gathered_prev) {
+  if (!c || !theta_dev) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->g_buf) return fail(PAYNE_E_INVALID, "payne_gather_create / payne_gather_connect first");
+  if (B != c->g_slots) return fail(PAYNE_E_INVALID, "batch size differs from the gather's slots per rank");
+  for (int r = 0; r < c->g_world; ++r)
+    if (!c->g_peer_buf[r]) return fail(PAYNE_E_INVALID, "payne_gather_connect first");
+  DeviceGuard dg(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long s = c->g_seq;                            // this step
+  const size_t per = (size_t)c->g_world * c->g_slots;      // doubles per buffer
+  double* mine = c->g_buf + (size_t)(s % 3) * per + (size_t)c->g_rank * c->g_slots;
+  // Buffer s % 3 was last read by the consumers of step s - 3, whose reads every rank enqueued before it submitted
+  // step s - 2; the push below starts only after every rank's push of step s - 1 has landed here, which on the
+  // peer's stream lies behind its submit of step s - 2: nobody still reads what is about to be overwritten.
+  int rc = run_batch(c, theta_dev, B, ld, nullptr, nullptr, mine, st);
+  if (rc) return rc;
+  GatherPush G{};
+  G.src = mine;
+  for (int r = 0; r < c->g_world; ++r) {
+    G.dst[r] = c->g_peer_buf[r] + (size_t)(s % 3) * per + (size_t)c->g_rank * c->g_slots;
+    G.flag[r] = c->g_peer_flag[r] + c->g_rank;
+  }
+  G.local_flags = c->g_flag;
+  G.wait_for = (unsigned long long)s;                      // step s - 1 complete <=> flags == s
+  G.raise_to = (unsigned long long)(s + 1);
+  G.world = c->g_world; G.rank = c->g_rank; G.n = (int)B; G.done = c->g_done; G.status = c->status;
+  gather_push_kernel<<<1, 1024, 0, st>>>(G);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  if (gathered_prev) *gathered_prev = s > 0 ? c->g_buf + (size_t)((s - 1) % 3) * per : nullptr;
+  c->g_seq = s + 1;
+  return mark_done(c, st);
+}
+
+int payne_gather_flush(PayneCtx* c, void* stream, double** gathered_last) {
+  if (!c || !gathered_last) return fail(PAYNE_E_INVALID, "null argument");
+  if (!c->g_buf || c->g_seq == 0) return fail(PAYNE_E_INVALID, "nothing submitted");
+  DeviceGuard dg(c->device);
+  gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c->g_flag, (unsigned long long)c->g_seq, c->g_world, c->status);
+  CU_TRY(cudaGetLastError());
+  *gathered_last = c->g_buf + (size_t)((c->g_seq - 1) % 3) * (size_t)c->g_world * c->g_slots;
   return PAYNE_OK;
 }
 
