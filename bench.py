@@ -146,6 +146,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        # NVML polling is not free for the polled GPU's process: at 8 GPUs a 2 ms period measured +7 us per 0.87 ms step
+        # against a 50 ms period (gpurun_out/r2_bench_n8c.json); 4 ms still gives 4-5 samples in the shortest runs
+        self.period = float(os.environ.get('BENCH_CLOCK_PERIOD', '0.004'))
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -172,7 +175,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def summary(self):
         return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_sm,
@@ -362,10 +365,16 @@ def run_ours(args):
     launches = eng.query('launches') - l0
     sampler.stop_flag = True
     sampler.join()
+    by_rank = None
     if world > 1:
-        t = torch.tensor([ms], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        # the step time is the MAX over ranks; every rank's own time and SM clock go into the line as well, so that a
+        # scaling loss can be told apart from one slow GPU of the box
+        mine = torch.tensor([ms, float(np.median(sampler.sm)) if sampler.sm else 0.0], device='cuda', dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = {'ms_per_step': [round(float(a[0].item()) / K, 5) for a in allr],
+                   'sm_mhz': [float(a[1].item()) for a in allr]}
+        ms = max(float(a[0].item()) for a in allr)
     n_finite = int(torch.isfinite(out).sum().item())
 
     # per-kernel device time (CUDA events on the launching stream inside the library)
@@ -504,6 +513,7 @@ def run_ours(args):
                 'path': 'payne_lnlike_batch_host (C ABI, host buffers)' if world == 1 else
                         'pinned theta -> H2D -> likelihood -> all-gather of lnL over %s -> D2H' % e2e_gather},
         'gpu_launches': int(launches),
+        'by_rank': by_rank,
         'roofline': {'kernel': 'tail_fast_kernel<%d> (+tail_setup_kernel)' % int(np.log2(eng.query('nfft1'))), 'bound': 'hbm', 'achieved': tail_gbs, 'peak': hbm, 'unit': 'GB/s',
                      'frac': tail_gbs / hbm, 'traffic': traffic, 'algorithmic_bytes': tail_bytes, 'peak_source': which, 'ms_per_launch': tail_ms,
                      'limiter': limiter,
