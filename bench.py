@@ -349,6 +349,18 @@ def run_ours(args):
     if world > 1:
         out = drain()
     barrier()
+    # N > 1: the same K steps WITHOUT the gather first -- every rank at its own pace.  With the gather the ranks are
+    # coupled (all run at the pace of the slowest GPU of the box); the uncoupled times tell that apart from a cost of
+    # the collective (by_rank in the line).
+    ms_free = None
+    if world > 1:
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(K):
+            eng.lnlike_batch(theta)
+        f1.record()
+        barrier()
+        ms_free = f0.elapsed_time(f1)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.query('launches')
@@ -369,10 +381,11 @@ def run_ours(args):
     if world > 1:
         # the step time is the MAX over ranks; every rank's own time and SM clock go into the line as well, so that a
         # scaling loss can be told apart from one slow GPU of the box
-        mine = torch.tensor([ms, float(np.median(sampler.sm)) if sampler.sm else 0.0], device='cuda', dtype=torch.float64)
+        mine = torch.tensor([ms, float(np.median(sampler.sm)) if sampler.sm else 0.0, ms_free], device='cuda', dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         by_rank = {'ms_per_step': [round(float(a[0].item()) / K, 5) for a in allr],
+                   'ms_per_step_without_gather': [round(float(a[2].item()) / K, 5) for a in allr],
                    'sm_mhz': [float(a[1].item()) for a in allr]}
         ms = max(float(a[0].item()) for a in allr)
     n_finite = int(torch.isfinite(out).sum().item())
