@@ -333,15 +333,31 @@ def run_ours(args):
 
     # N > 1: the all-gather of step i runs on a side stream beside the kernels of step i + 1
     # (thepayne_b200.dist.PipelinedGather); the timed region ends only after the last gather has landed
+    # N > 1: the library's own all-gather fused into the tail kernel (payne_lnlike_batch_gather: the thread that writes a
+    # point's lnL stores it into every peer's buffer over NVLink, the last CTA raises the flags).  Measured on one 8 x B200
+    # box, same run: 0.8626 ms/step against 0.8729 with ncclAllGather on a side stream one step behind
+    # (BENCH_GATHER=nccl, the fallback when peer memory cannot be mapped); 0.853-0.857 per rank without any gather.
     pg = pdist.PipelinedGather() if world > 1 else None
+    gather_kind = 'ncclAllGather on a side stream, one step behind (dist.PipelinedGather)' if world > 1 else None
+    peer_main = None
+    if world > 1 and os.environ.get('BENCH_GATHER', 'peer') == 'peer':
+        try:
+            peer_main = pdist.PeerGather(eng, B)
+            gather_kind = 'peer memory, fused into the tail kernel (dist.PeerGather)'
+        except Exception:
+            peer_main = None
 
     def step():
+        if peer_main is not None:
+            return peer_main.submit(theta)
         lnl = eng.lnlike_batch(theta)
         if world == 1:
             return lnl
         return pg.submit(lnl)
 
     def drain():
+        if peer_main is not None:
+            return peer_main.flush()
         return pg.flush()[-1] if world > 1 else None
 
     for _ in range(max(W, 3)):
@@ -413,7 +429,7 @@ def run_ours(args):
         # every step needs ITS gathered vector (nothing to pipeline behind): the library's own all-gather over peer
         # memory (payne_gather_*: one push kernel + flags, ~13 us at 8 GPUs) instead of a blocking ncclAllGather
         try:
-            peer = pdist.PeerGather(eng, B)
+            peer = peer_main if peer_main is not None else pdist.PeerGather(eng, B)
             e2e_gather = 'peer memory (payne_lnlike_batch_gather + payne_gather_flush)'
         except Exception as exc:                     # raised on every rank alike
             peer, e2e_gather = None, 'ncclAllGather (peer memory unavailable: %s)' % str(exc)[:80]
@@ -526,7 +542,7 @@ def run_ours(args):
                 'path': 'payne_lnlike_batch_host (C ABI, host buffers)' if world == 1 else
                         'pinned theta -> H2D -> likelihood -> all-gather of lnL over %s -> D2H' % e2e_gather},
         'gpu_launches': int(launches),
-        'by_rank': by_rank,
+        'by_rank': by_rank, 'gather': gather_kind,
         'roofline': {'kernel': 'tail_fast_kernel<%d> (+tail_setup_kernel)' % int(np.log2(eng.query('nfft1'))), 'bound': 'hbm', 'achieved': tail_gbs, 'peak': hbm, 'unit': 'GB/s',
                      'frac': tail_gbs / hbm, 'traffic': traffic, 'algorithmic_bytes': tail_bytes, 'peak_source': which, 'ms_per_launch': tail_ms,
                      'limiter': limiter,

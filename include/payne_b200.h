@@ -185,9 +185,12 @@ int payne_ann_eval(PayneCtx* ctx, const double* x_dev, int64_t B, float* y_dev, 
  * world * slots doubles.  payne_gather_create allocates them and writes PAYNE_GATHER_HANDLE_BYTES of CUDA IPC handles to
  * handles_out; the ranks exchange those bytes (any transport: the Python side uses torch.distributed's all_gather_object)
  * and pass the concatenation, in rank order, to payne_gather_connect, which maps the peers' buffers (NVLink P2P).
- * payne_lnlike_batch_gather = payne_lnlike_batch of this rank's B = slots points, its lnL written into this rank's slice
- * and pushed into every rank's buffer by one kernel (plain stores through the peer mappings, then a flag per rank behind a
- * system-scope fence); stream-ordered, no host synchronisation, every rank must call it the same number of times.
+ * payne_lnlike_batch_gather = payne_lnlike_batch of this rank's B = slots points with the all-gather fused into the tail
+ * kernel: the thread that writes a point's lnL also stores it into every rank's buffer (plain stores through the peer
+ * mappings), and the last CTA of the kernel raises this rank's flag on every rank behind a system-scope fence (tails
+ * without the hook -- general grid, LSF, photometry only -- are followed by one small push kernel doing the same);
+ * stream-ordered, no host synchronisation, every rank must call it the same number of times.
+ * PAYNE_GATHER_FUSED=0 (environment): always the separate push kernel.
  * *gathered_prev receives the device pointer of the complete gathered vector [world * slots] of the PREVIOUS call (NULL on
  * the first): it is valid for work enqueued on `stream` after this call and must be consumed before the next call.
  * payne_gather_flush enqueues the wait for the last step and returns its vector.  A peer that never arrives sets

@@ -184,7 +184,11 @@ struct PayneCtx {
   double* g_peer_buf[16] = {nullptr};           // every rank's g_buf as mapped into this process (own = local)
   unsigned long long* g_peer_flag[16] = {nullptr};
   bool g_opened[16] = {false};
-  int* g_done = nullptr;                        // CTA counter of the push kernel
+  int* g_done = nullptr;                        // CTA counter of the fused tail's exit
+  bool g_fuse = true;                           // PAYNE_GATHER_FUSED=0: always the separate push kernel
+  bool g_active = false, g_fused = false;       // set around run_batch by payne_lnlike_batch_gather
+  unsigned long long g_wait_for = 0, g_raise_to = 0;
+  size_t g_bufoff = 0;
   // host staging
   long long stage_cap = 0, stage_ld = 0;
   double *theta_pin = nullptr, *lnl_pin = nullptr, *theta_stage = nullptr, *lnl_stage = nullptr;
@@ -769,6 +773,8 @@ int run_mlp(PayneCtx* c, const payne::EncodeParams& E, const double* x, long lon
   return PAYNE_OK;
 }
 
+__global__ void gather_wait_kernel(const unsigned long long* flags, unsigned long long wait_for, int world, int* status);
+
 int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, double* flux_out,
               double* mags_out, double* lnl, cudaStream_t st) {
   using namespace payne;
@@ -790,12 +796,22 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
     int is_depth = 0;
     const bool fast_tail = c->has_spec && c->use_fast && c->allow_fast && !c->lsf_on;
     TailParams T = c->tail;
+    const bool gather_here = c->g_active && c->g_fuse && fast_tail;
     if (c->has_spec) {
       T.theta = th; T.ld = ld; T.flux = c->flux; T.ldf = c->ldf; T.B = nb;
       T.chi2_sed = c->has_phot ? c->chi2_sed : nullptr;
       T.lnl = lnl ? lnl + p0 : nullptr;
       T.model_out = flux_out ? flux_out + p0 * T.n_obs : nullptr;
       T.status = c->status;
+      if (gather_here) {
+        // all-gather fused into the tail (tail.cuh store_lnl / gather_exit): this slab's slice of every peer's buffer
+        T.g_world = c->g_world; T.g_rank = c->g_rank; T.g_done = c->g_done;
+        for (int r = 0; r < c->g_world; ++r) {
+          T.g_dst[r] = r == c->g_rank ? nullptr : c->g_peer_buf[r] + c->g_bufoff + (size_t)c->g_rank * c->g_slots + p0;
+          T.g_flag[r] = c->g_peer_flag[r] + c->g_rank;
+        }
+        T.g_raise = (p0 + c->slab >= B) ? c->g_raise_to : 0ull;
+      }
       if (fast_tail) {
         // per-point setup depends only on theta: fork it beside the emulator GEMMs, join before the tail
         CU_TRY(cudaEventRecord(c->ev_fork, st));
@@ -804,6 +820,10 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
                                                                   : std::min(c->tail_grid_fast, nb);
         if (c->grid_cap > 0) c->fast.work_start = std::min(c->fast.work_start, c->grid_cap);
         if (payne::launch_tail_setup(nb, c->side, T, c->fast)) return fail(PAYNE_E_CUDA, "tail_setup launch");
+        if (gather_here && p0 == 0 && c->g_wait_for)
+          // the buffer the tail is about to write on the peers is free once every rank's previous step has landed here;
+          // waited for on the side stream, beside the emulator GEMMs
+          gather_wait_kernel<<<1, 32, 0, c->side>>>(c->g_flag, c->g_wait_for, c->g_world, c->status);
         CU_TRY(cudaEventRecord(c->ev_join, c->side));
         c->launches++;
       }
@@ -848,10 +868,12 @@ int run_batch(PayneCtx* c, const double* theta, long long B, long long ld, doubl
         FC.win_floats = c->cluster_win_floats;
         if (payne::launch_tail_cluster(T.log2N1, c->fast.work_start, c->cluster_smem, st, T, FC))
           return fail(PAYNE_E_CUDA, "tail launch");
+        if (gather_here && T.g_raise) c->g_fused = true;
       } else if (fast_tail && is_depth) {
         const int grid = c->fast.work_start;
         const bool poly = T.n_poly != 0 || T.model_out != nullptr;
         if (payne::launch_tail_fast(T.log2N1, poly, grid, c->fast_smem, st, T, c->fast)) return fail(PAYNE_E_CUDA, "tail launch");
+        if (gather_here && T.g_raise) c->g_fused = true;
       } else {
         if (c->tail.log2N1 > 15) return fail(PAYNE_E_UNSUPPORTED, "general-grid tail is limited to 32768-point transforms");
         const int grid = std::min(c->tail_grid, nb);
@@ -1069,6 +1091,7 @@ int payne_gather_create(PayneCtx* c, int world, int rank, int64_t slots, void* h
   if (c->g_buf) return fail(PAYNE_E_INVALID, "gather already created on this context");
   DeviceGuard dg(c->device);
   c->g_world = world; c->g_rank = rank; c->g_slots = slots; c->g_seq = 0;
+  { const char* e = getenv("PAYNE_GATHER_FUSED"); c->g_fuse = !(e && e[0] == '0'); }
   const size_t nb = (size_t)3 * world * slots * sizeof(double);
   CU_TRY(cudaMalloc((void**)&c->g_buf, nb));
   CU_TRY(cudaMemset(c->g_buf, 0, nb));
@@ -1119,8 +1142,15 @@ int payne_lnlike_batch_gather(PayneCtx* c, const double* theta_dev, int64_t B, i
   // Buffer s % 3 was last read by the consumers of step s - 3, whose reads every rank enqueued before it submitted
   // step s - 2; the push below starts only after every rank's push of step s - 1 has landed here, which on the
   // peer's stream lies behind its submit of step s - 2: nobody still reads what is about to be overwritten.
+  c->g_active = true; c->g_fused = false;
+  c->g_wait_for = (unsigned long long)s; c->g_raise_to = (unsigned long long)(s + 1);
+  c->g_bufoff = (size_t)(s % 3) * per;
   int rc = run_batch(c, theta_dev, B, ld, nullptr, nullptr, mine, st);
+  c->g_active = false;
   if (rc) return rc;
+  if (gathered_prev) *gathered_prev = s > 0 ? c->g_buf + (size_t)((s - 1) % 3) * per : nullptr;
+  c->g_seq = s + 1;
+  if (c->g_fused) return PAYNE_OK;          // the tail stored the slice on the peers and raised the flags itself
   GatherPush G{};
   G.src = mine;
   for (int r = 0; r < c->g_world; ++r) {
@@ -1134,8 +1164,6 @@ int payne_lnlike_batch_gather(PayneCtx* c, const double* theta_dev, int64_t B, i
   gather_push_kernel<<<1, 1024, 0, st>>>(G);
   CU_TRY(cudaGetLastError());
   c->launches++;
-  if (gathered_prev) *gathered_prev = s > 0 ? c->g_buf + (size_t)((s - 1) % 3) * per : nullptr;
-  c->g_seq = s + 1;
   return mark_done(c, st);
 }
 

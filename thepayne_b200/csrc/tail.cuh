@@ -80,7 +80,33 @@ struct TailParams {
   int rows_may_nan;         // rows can hold NaN although the labels are finite (continuum emulator attached)
   int debug_skip;           // profiling aid (fast tail): bit0/1 skip stage 1/2 (regrid in + transforms),
                             // bit3 the regrid back, bit4 the final pass; results are garbage
+  // Multi-GPU all-gather of lnL fused into the tail (payne_lnlike_batch_gather; fast and cluster tails): the thread
+  // that writes a point's lnL also stores it into every peer's gathered buffer through the NVLink peer mappings, and
+  // the last CTA to leave the kernel raises this rank's flag on every rank behind a system-scope fence.  g_world = 0: off.
+  // (at the END of the struct: the fields above keep the constant-bank offsets the kernels were tuned with)
+  int g_world, g_rank;
+  double* g_dst[16];                 // rank r's buffer of this step at this rank's slice, slab offset included
+  unsigned long long* g_flag[16];    // rank r's flag word of this rank
+  unsigned long long g_raise;        // 0: this launch does not finish the step (a slab before the last one)
+  int* g_done;                       // CTA counter (zero between launches)
 };
+
+// lnL of point p: local result and, with the fused gather on, the copy in every peer's buffer
+__device__ __forceinline__ void store_lnl(const TailParams& P, int p, double v) {
+  P.lnl[p] = v;
+  for (int r = 0; r < P.g_world; ++r)
+    if (r != P.g_rank) P.g_dst[r][p] = v;
+}
+// every CTA, once, behind its last point (thread 0): the CTA's peer stores are fenced; the last CTA raises the flags
+__device__ __forceinline__ void gather_exit(const TailParams& P, unsigned nctas) {
+  if (P.g_world == 0) return;
+  __threadfence_system();
+  if (P.g_raise && atomicAdd(P.g_done, 1) == (int)nctas - 1) {
+    *P.g_done = 0;
+    __threadfence_system();
+    for (int r = 0; r < P.g_world; ++r) *reinterpret_cast<volatile unsigned long long*>(P.g_flag[r]) = P.g_raise;
+  }
+}
 
 struct PointSetup {
   double vsini_scale;   // |vsini| * sb_scale

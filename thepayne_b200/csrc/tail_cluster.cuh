@@ -392,7 +392,7 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
       if (rank == 0) {
         if (P.model_out)
           for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
-        if (tid == 0 && P.lnl) P.lnl[p] = nan;
+        if (tid == 0 && P.lnl) store_lnl(P, p, nan);
       }
       cl::cluster_sync();
       pn = c_next[it];
@@ -497,7 +497,7 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
     if (rank == 0 && tid == 0 && P.lnl) {
       double c2 = (cred[0] + cred[1]) + (cred[2] + cred[3]);
       if (P.chi2_sed) c2 += P.chi2_sed[p];
-      P.lnl[p] = -0.5 * c2;
+      store_lnl(P, p, -0.5 * c2);
     }
     // the consumed row is dropped from L2 without write-back (tail_fast.cuh); each CTA drops a quarter
     if (P.discard_rows) {
@@ -505,6 +505,7 @@ tail_cluster_kernel(const __grid_constant__ TailParams P, const __grid_constant_
       discard_lines(row + a, b - a, tid);
     }
   }
+  if (tid == 0) gather_exit(P, gridDim.x);
 }
 
 }  // namespace payne

@@ -380,7 +380,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     if (S.bad) {
       if (P.model_out)
         for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
-      if (tid == 0 && P.lnl) P.lnl[p] = nan;
+      if (tid == 0 && P.lnl) store_lnl(P, p, nan);
       __syncthreads();
       continue;
     }
@@ -504,7 +504,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
 #pragma unroll
       for (int wdx = 0; wdx < kNT / 32; ++wdx) c2 += red[wdx];
       if (P.chi2_sed) c2 += P.chi2_sed[p];
-      P.lnl[p] = -0.5 * c2;
+      store_lnl(P, p, -0.5 * c2);
     }
     // The row is scratch and fully consumed: L2 is told to drop its lines instead of writing them back
     // (discard.global.L2).  Without this every row crosses HBM three times (the emulator's write is evicted --
@@ -514,6 +514,7 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
     if (P.discard_rows) discard_lines(row, P.n, tid);
     __syncthreads();
   }
+  if (tid == 0) gather_exit(P, gridDim.x);
 }
 
 // One thread per point: mask limits, transform sizes, Doppler factor, taper constant, and the
