@@ -1030,7 +1030,6 @@ struct GatherPush {
   unsigned long long wait_for;       // flags must have reached this value (0: nothing to wait for)
   unsigned long long raise_to;
   int world, rank, n;
-  int* done;
   int* status;
 };
 
@@ -1160,7 +1159,7 @@ int payne_lnlike_batch_gather(PayneCtx* c, const double* theta_dev, int64_t B, i
   G.local_flags = c->g_flag;
   G.wait_for = (unsigned long long)s;                      // step s - 1 complete <=> flags == s
   G.raise_to = (unsigned long long)(s + 1);
-  G.world = c->g_world; G.rank = c->g_rank; G.n = (int)B; G.done = c->g_done; G.status = c->status;
+  G.world = c->g_world; G.rank = c->g_rank; G.n = (int)B; G.status = c->status;
   gather_push_kernel<<<1, 1024, 0, st>>>(G);
   CU_TRY(cudaGetLastError());
   c->launches++;
