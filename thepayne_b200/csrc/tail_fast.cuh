@@ -31,6 +31,12 @@
 // A second, window-only instantiation of the rotation filter for points whose whole table range is staged (no per-lookup
 // choice, no table-end test) measured 1 % SLOWER at C2 both in round 2's first build (1.7 %) and with the shared passes
 // (0.6825 -> 0.689 ms, A/B on one box): off.
+// L2 prefetch (cp.async.bulk.prefetch.L2) of the row a CTA will work on next, issued when the point is claimed: measured
+// 0.6 % SLOWER at C2 (0.6823 -> 0.6864 ms, A/B on one box) -- with three CTAs per SM in different phases the row loads of the
+// fused first pass already overlap other CTAs' work, and the early fetch competes for L2 with rows still in use.  Off.
+#ifndef PAYNE_TAIL_PREFETCH
+#define PAYNE_TAIL_PREFETCH 0
+#endif
 #ifndef PAYNE_ROT_WINONLY
 #define PAYNE_ROT_WINONLY 0
 #endif
@@ -377,6 +383,14 @@ tail_fast_kernel(const __grid_constant__ TailParams P, const __grid_constant__ F
       reinterpret_cast<int4*>(&SP)[tid] = __ldg(reinterpret_cast<const int4*>(points + p) + tid);
     __syncthreads();
     pn = s_next;
+#if PAYNE_TAIL_PREFETCH
+    // the row of the point this CTA will work on next: from HBM into L2 now, so that its first pass finds it there
+    // (the slab is larger than L2: every row's first touch is a DRAM access otherwise)
+    if (tid == 0 && pn < P.B) {
+      const float* nrow = P.flux + (long long)pn * P.ldf;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrow), "r"((unsigned)((P.n * 4) & ~15)) : "memory");
+    }
+#endif
     if (S.bad) {
       if (P.model_out)
         for (int j = tid; j < P.n_obs; j += kNT) P.model_out[(long long)p * P.n_obs + j] = nan;
