@@ -79,3 +79,24 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 txt = open(os.path.join(dp, f)).read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt, os.path.join(dp, f)
+
+
+def test_build_units_and_their_headers_exist():
+    """thepayne_b200/build.py: every translation unit and every header its staleness check lists is in csrc/ (a
+    header renamed without updating the table would silently stop triggering rebuilds)."""
+    from thepayne_b200 import build as b
+    for unit, hdrs in b.UNITS.items():
+        assert os.path.exists(os.path.join(b.CSRC, unit)), unit
+        for h in hdrs:
+            assert os.path.exists(os.path.join(b.CSRC, h)), (unit, h)
+    import glob
+    on_disk = {os.path.basename(p) for p in glob.glob(os.path.join(b.CSRC, '*.cu'))}
+    assert on_disk == set(b.UNITS), (on_disk, set(b.UNITS))
+
+
+def test_peer_gather_needs_a_process_group():
+    from thepayne_b200 import dist as pdist
+    with pytest.raises(RuntimeError):
+        pdist.PeerGather(None, 16)
+    a = pdist._DevArray(0x1000, 8).__cuda_array_interface__
+    assert a['shape'] == (8,) and a['typestr'] == '<f8' and a['data'] == (0x1000, False)
