@@ -1,5 +1,14 @@
 """Dev tool: the cluster-distributed tail (tail_cluster.cuh) against the single-CTA split tail on the same points
-(golden c4m rows + a drawn batch), with the tail time of both."""
+(golden c4m rows + a drawn batch), with the tail time of both.
+
+Per-phase clocks (profiles/r02_cluster_tail.txt) come from an instrumented build of the one translation unit, linked with
+the other objects of a normal build and selected with PAYNE_LIB_PATH:
+    cd thepayne_b200/csrc
+    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DPAYNE_CLUSTER_PROF \
+         -c -o /tmp/tc_prof.o tail_cluster_tu.cu
+    nvcc -shared -gencode arch=compute_100a,code=sm_100a -o _build/libpayne_prof.so _build/payne_b200.o _build/gemm_tu.o \
+         _build/tail_fast_tu.o _build/tail_fast_poly_tu.o _build/tail_general_tu.o /tmp/tc_prof.o
+    PAYNE_LIB_PATH=$PWD/_build/libpayne_prof.so python tools/gpu_cluster.py c4m 4096"""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
