@@ -24,7 +24,10 @@
 //   The four partial chi2 meet in CTA 0 (st.shared::cluster + cluster barrier, fixed summation order).
 //
 // All CTAs of a cluster read the same per-point record, so every branch around a cluster barrier is uniform
-// across the cluster.
+// across the cluster.  Points are handed out dynamically (CTA 0 claims the cluster's next point from a device counter
+// and posts it to its peers, published by the point's last barrier); with the multi-GPU gather on, CTA 0's thread 0
+// also stores the point's lnL into the other GPUs' buffers (tail.cuh store_lnl / gather_exit).
+// compute-sanitizer (memcheck, racecheck, synccheck, initcheck) is clean on this kernel: profiles/r02_sanitizer.txt.
 #pragma once
 #include "tail_fast.cuh"
 
